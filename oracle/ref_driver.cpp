@@ -1,0 +1,287 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Driver around the reference's own hot-path functions (bcgsc/arcs 1.2.8), which
+// build_ref.sh extracts verbatim by line range from /root/reference/Arcs/Arcs.{h,cpp}
+// into ref_types.inc / ref_part_a.inc / ref_part_b.inc in a temp dir.  Everything in
+// THIS file is ours: argument parsing for the ARKS subset of the arcs CLI, dumps of
+// the intermediate containers (kmap / per-read conreci trace / imap / pmap), phase
+// timing for the CPU baseline, and a Boost-free restatement of createGraph +
+// boost::write_graphviz (Arcs.cpp:1475-1526,1549-1610; text format pinned by
+// Examples/arks_test-demo/output/*_original.gv).
+#include <algorithm>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <getopt.h>
+#include <iostream>
+#include <iterator>
+#include <limits>
+#include <map>
+#include <omp.h>
+#include <sstream>
+#include <string>
+#include <time.h>
+#include <tuple>
+#include <unistd.h>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+#include <zlib.h>
+
+#include "Common/IOUtil.h"
+#include "Common/ReadsProcessor.h"
+#include "kseq.h"
+
+#include "ref_types.inc" // opens namespace ARCS, ArcsParams .. ContigToLengthIt
+// google::sparse_hash_map stand-in.  The reference only ever find()s / operator[]s
+// this map (Arcs.cpp:903-917,969-971), so the container is not result-bearing.
+struct ContigKMap : std::unordered_map<std::string, int>
+{
+	void set_deleted_key(const std::string&) {}
+};
+} // namespace ARCS
+
+static ARCS::ArcsParams params;
+
+#include "ref_part_a.inc" // counters .. bestContig
+
+// Interpose on bestContig so the per-read decision can be traced (only meaningful at -t 1).
+static FILE* g_trace = NULL;
+static int
+bestContig_traced(ARCS::ContigKMap& kmap, std::string readseq, int k, double j, ReadsProcessor& proc)
+{
+	int r = bestContig(kmap, readseq, k, j, proc);
+	if (g_trace)
+		fprintf(g_trace, "%d\n", r);
+	return r;
+}
+#define bestContig bestContig_traced
+#include "ref_part_b.inc" // getContigKmers .. checkSignificance, TSV writers
+#undef bestContig
+
+// ---- Boost-free createGraph / removeDegreeNodes / write_graphviz restatement ----
+struct RefEdge
+{
+	int u, v, orientation, weight;
+};
+struct RefGraph
+{
+	std::vector<std::string> vid;
+	std::vector<RefEdge> edges;
+};
+
+static void
+createGraphNoBoost(const ARCS::PairMap& pmap, RefGraph& g)
+{
+	std::unordered_map<std::string, int> vmap;
+	for (auto it = pmap.begin(); it != pmap.end(); ++it) {
+		unsigned max, index;
+		std::tie(max, index) = getMaxValueAndIndex(it->second);
+		unsigned second = 0;
+		for (unsigned i = 0; i < it->second.size(); ++i)
+			if (it->second[i] != max && it->second[i] > second)
+				second = it->second[i];
+		if (checkSignificance(max, max + second)) {
+			for (const std::string* s : { &it->first.first, &it->first.second })
+				if (!vmap.count(*s)) {
+					vmap[*s] = (int)g.vid.size();
+					g.vid.push_back(*s);
+				}
+			g.edges.push_back({ vmap[it->first.first], vmap[it->first.second], (int)index, (int)max });
+		}
+	}
+}
+
+static void
+writeGraphNoBoost(const std::string& path, RefGraph g, int max_degree)
+{
+	if (max_degree != 0) {
+		std::vector<int> deg(g.vid.size(), 0);
+		for (auto& e : g.edges) {
+			deg[e.u]++;
+			deg[e.v]++;
+		}
+		std::vector<int> remap(g.vid.size(), -1);
+		std::vector<std::string> nv;
+		for (size_t i = 0; i < g.vid.size(); ++i)
+			if (deg[i] <= max_degree) {
+				remap[i] = (int)nv.size();
+				nv.push_back(g.vid[i]);
+			}
+		std::vector<RefEdge> ne;
+		for (auto& e : g.edges)
+			if (remap[e.u] >= 0 && remap[e.v] >= 0)
+				ne.push_back({ remap[e.u], remap[e.v], e.orientation, e.weight });
+		g.vid.swap(nv);
+		g.edges.swap(ne);
+	}
+	std::ofstream out(path.c_str());
+	out << "graph G {\n";
+	for (size_t i = 0; i < g.vid.size(); ++i)
+		out << i << " [id=" << g.vid[i] << "];\n";
+	for (auto& e : g.edges)
+		out << e.u << "--" << e.v << " [label=" << e.orientation << ", weight=" << e.weight << "];\n";
+	out << "}\n";
+}
+
+static std::string
+hexkey(const std::string& s)
+{
+	static const char* d = "0123456789abcdef";
+	std::string o;
+	for (unsigned char c : s) {
+		o += d[c >> 4];
+		o += d[c & 15];
+	}
+	return o;
+}
+
+static double
+now()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int
+main(int argc, char** argv)
+{
+	std::string dump_kmap, dump_trace, dump_imap, dump_pmap, timing_json;
+	static const struct option lo[] = { { "dump-kmap", required_argument, NULL, 1001 },
+		                                { "dump-trace", required_argument, NULL, 1002 },
+		                                { "dump-imap", required_argument, NULL, 1003 },
+		                                { "dump-pmap", required_argument, NULL, 1004 },
+		                                { "timing-json", required_argument, NULL, 1005 },
+		                                { "arks", no_argument, NULL, 1006 },
+		                                { "tsv", required_argument, NULL, 1007 },
+		                                { "barcode-counts", required_argument, NULL, 1008 },
+		                                { NULL, 0, NULL, 0 } };
+	params.arks = true;
+	for (int c; (c = getopt_long(argc, argv, "f:c:l:z:b:m:d:e:r:vt:u:j:k:", lo, NULL)) != -1;) {
+		std::istringstream arg(optarg != NULL ? optarg : "");
+		switch (c) {
+		case 'u': arg >> params.multfile; break;
+		case 'k': arg >> params.k_value; break;
+		case 'j': arg >> params.j_index; break;
+		case 't': arg >> params.threads; break;
+		case 'f': arg >> params.file; break;
+		case 'c': arg >> params.min_reads; break;
+		case 'l': arg >> params.min_links; break;
+		case 'z': arg >> params.min_size; break;
+		case 'b': arg >> params.base_name; break;
+		case 'm': {
+			std::string a, b;
+			std::getline(arg, a, '-');
+			std::getline(arg, b);
+			std::stringstream ss;
+			ss << a << "\t" << b;
+			ss >> params.min_mult >> params.max_mult;
+		} break;
+		case 'd': arg >> params.max_degree; break;
+		case 'e': arg >> params.end_length; break;
+		case 'r': arg >> params.error_percent; break;
+		case 'v': ++params.verbose; break;
+		case 1001: dump_kmap = optarg; break;
+		case 1002: dump_trace = optarg; break;
+		case 1003: dump_imap = optarg; break;
+		case 1004: dump_pmap = optarg; break;
+		case 1005: timing_json = optarg; break;
+		case 1006: break;
+		case 1007: params.tsv_name = optarg; break;
+		case 1008: params.barcode_counts_name = optarg; break;
+		default: return 2;
+		}
+	}
+	std::vector<std::string> filenames(argv + optind, argv + argc);
+	if (params.file.empty() || filenames.empty() || params.base_name.empty()) {
+		fprintf(stderr, "usage: arcs_ref -f contigs.fa -b base [arcs --arks options] reads.fq[.gz]...\n");
+		return 2;
+	}
+	omp_set_num_threads(params.threads);
+
+	ARCS::IndexMap imap;
+	ARCS::PairMap pmap;
+	std::unordered_map<std::string, int> indexMultMap;
+	ARCS::ContigKMap kmap;
+	kmap.set_deleted_key("");
+	ARCS::ContigToLength contigToLength;
+	std::vector<ARCS::CI> contigRecord;
+
+	double t0 = now();
+	if (!params.multfile.empty())
+		createIndexMultMap(params.multfile, indexMultMap);
+	else
+		readBarcodes(filenames, indexMultMap);
+	double t1 = now();
+	contigRecord.resize(initContigArray(params.file));
+	getContigKmers(params.file, kmap, contigRecord, contigToLength);
+	double t2 = now();
+	if (!dump_trace.empty())
+		g_trace = fopen(dump_trace.c_str(), "w");
+	readChroms(filenames, kmap, imap, indexMultMap, contigRecord);
+	if (g_trace)
+		fclose(g_trace);
+	double t3 = now();
+	pairContigs(imap, pmap, indexMultMap);
+	double t4 = now();
+	RefGraph g;
+	createGraphNoBoost(pmap, g);
+	writeGraphNoBoost(params.base_name + "_original.gv", g, params.max_degree);
+	double t5 = now();
+	if (!params.tsv_name.empty()) {
+		size_t barcodeCount = countBarcodes(imap, indexMultMap);
+		writeTSV(params.tsv_name, imap, pmap, barcodeCount);
+	}
+	if (!params.barcode_counts_name.empty())
+		writeBarcodeCountsTSV(params.barcode_counts_name, indexMultMap);
+
+	if (!dump_kmap.empty()) {
+		std::vector<std::pair<std::string, int>> v(kmap.begin(), kmap.end());
+		std::sort(v.begin(), v.end());
+		FILE* f = fopen(dump_kmap.c_str(), "w");
+		for (auto& e : v)
+			fprintf(f, "%s\t%d\n", hexkey(e.first).c_str(), e.second);
+		fclose(f);
+	}
+	if (!dump_imap.empty()) {
+		std::vector<std::string> lines;
+		for (auto& b : imap)
+			for (auto& s : b.second) {
+				std::ostringstream o;
+				o << b.first << '\t' << s.first.first << '\t' << (s.first.second ? 'H' : 'T') << '\t' << s.second;
+				lines.push_back(o.str());
+			}
+		std::sort(lines.begin(), lines.end());
+		FILE* f = fopen(dump_imap.c_str(), "w");
+		for (auto& l : lines)
+			fprintf(f, "%s\n", l.c_str());
+		fclose(f);
+	}
+	if (!dump_pmap.empty()) {
+		FILE* f = fopen(dump_pmap.c_str(), "w");
+		for (auto& it : pmap)
+			fprintf(f, "%s\t%s\t%u\t%u\t%u\t%u\n", it.first.first.c_str(), it.first.second.c_str(),
+			        it.second[0], it.second[1], it.second[2], it.second[3]);
+		fclose(f);
+	}
+	// machine-readable counters + phase times (CPU baseline of bench.py reads this)
+	FILE* tj = timing_json.empty() ? stdout : fopen(timing_json.c_str(), "w");
+	fprintf(tj,
+	        "{\"threads\": %u, \"t_multiplicity_s\": %.6f, \"t_index_s\": %.6f, \"t_map_s\": %.6f, "
+	        "\"t_pair_s\": %.6f, \"t_graph_s\": %.6f, \"contig_kmers\": %u, \"null_kmers\": %u, "
+	        "\"recorded\": %u, \"collisions\": %u, \"removed\": %u, \"unique\": %u, "
+	        "\"read_kmers_valid\": %u, \"read_kmers_invalid\": %u, \"found\": %u, \"rec\": %u, "
+	        "\"dups\": %u, \"pass_jaccard\": %u, \"fail_jaccard\": %u, \"pmap_size\": %zu, "
+	        "\"imap_barcodes\": %zu}\n",
+	        params.threads, t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4,
+	        s_numkmersmapped + s_numkmercollisions, s_numbadkmers, s_numkmersmapped, s_numkmercollisions,
+	        s_numkmersremdup, s_uniquedraftkmers, s_totalnumckmers, s_numbadckmers, s_numckmersfound,
+	        s_numckmersrec, s_ckmersasdups, s_numreadspassingjaccard, s_numreadsfailjaccard, pmap.size(),
+	        imap.size());
+	if (tj != stdout)
+		fclose(tj);
+	return 0;
+}
