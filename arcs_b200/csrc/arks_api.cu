@@ -1,0 +1,962 @@
+// arks_api.cu -- the extern "C" boundary of libarks_b200.so (include/arks_b200.h):
+// handle, device memory, stream/event plumbing and kernel launches.  No torch types, no
+// CPU fallback: every entry point either runs the sm_100a kernels or fails loudly.
+#include "../../include/arks_b200.h"
+#include "arks_device.cuh"
+#include "arks_index.cuh"
+#include "arks_links.cuh"
+#include "arks_map.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace arks;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+};
+
+struct MapSlot
+{
+	DevBuf bases, off, bc, out;
+	cudaEvent_t copied = nullptr, done = nullptr;
+	bool busy = false;
+};
+
+} // namespace
+
+struct arks_handle
+{
+	int device = 0;
+	int k = 0, kw = 0;
+	uint64_t mask_hi = 0, mask_lo = 0;
+	int sm_count = 148;
+	cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+	// index
+	uint8_t* table = nullptr;
+	uint64_t nslots = 0;
+	bool finalized = false;
+	IndexCounters* d_ictr = nullptr;
+	arks_index_stats istats{};
+	DevBuf ib_bases, ib_off, ib_conreci, ib_inv, ib_skip, ib_tiles;
+	// map
+	MapCounters* d_mctr = nullptr;
+	MapSlot slots[2];
+	int next_slot = 0;
+	uint32_t* d_remap = nullptr;
+	uint32_t n_remap = 0;
+	int map_grid = 0;
+	// imap
+	unsigned long long* imap = nullptr;
+	uint64_t imap_cap = 0;
+	unsigned long long* d_imap_count = nullptr;
+	uint64_t imap_upper = 0; // host-side upper bound on the number of rows
+	// pmap
+	unsigned long long* pmap = nullptr;
+	uint64_t pmap_cap = 0;
+	unsigned long long* d_pmap_count = nullptr;
+	std::vector<uint32_t> pm_a, pm_b, pm_counts; // sorted host copy
+	bool pmap_ready = false;
+	// misc
+	unsigned long long* d_scratch = nullptr; // 8 x u64 scratch counters
+	std::string err;
+	uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(arks_handle* h, int code, const std::string& msg)
+{
+	if (h)
+		h->err = msg;
+	else
+		g_create_error = msg;
+	return code;
+}
+
+#define CU(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess)                                                                            \
+			return fail(h, ARKS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+	} while (0)
+
+int ensure(arks_handle* h, DevBuf& b, size_t bytes)
+{
+	if (b.cap >= bytes && b.p)
+		return ARKS_OK;
+	if (b.p) {
+		CU(cudaStreamSynchronize(h->stream));
+		CU(cudaFree(b.p));
+		b.p = nullptr;
+		b.cap = 0;
+	}
+	size_t want = bytes + bytes / 4 + 256;
+	CU(cudaMalloc(&b.p, want));
+	b.cap = want;
+	return ARKS_OK;
+}
+
+int grid_for(const arks_handle* h, uint64_t work_items, int block, int per_sm)
+{
+	uint64_t blocks = (work_items + block - 1) / block;
+	uint64_t cap = (uint64_t)h->sm_count * per_sm;
+	return (int)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+void key_masks(int k, uint64_t& mhi, uint64_t& mlo)
+{
+	int bits = 2 * k;
+	if (bits >= 64) {
+		mhi = ~0ull;
+		int r = bits - 64;
+		mlo = r == 0 ? 0ull : (r == 64 ? ~0ull : ~(~0ull >> r));
+	} else {
+		mhi = ~(~0ull >> bits);
+		mlo = 0;
+	}
+}
+
+// headOrTail's predicate (Arcs/Arcs.cpp:833-861) with the reference's exact types:
+// mean, sd float; std::sqrt(2) double; std::erf double; result narrowed to float.
+float normal_estimation(int x, float p, int n)
+{
+	float mean = n * p;
+	float sd = std::sqrt(n * p * (1 - p));
+	return 0.5 * (1 + std::erf((x - mean) / (sd * std::sqrt(2))));
+}
+
+bool ht_valid(int mx, int sum, int min_reads, float error_percent)
+{
+	if (sum < min_reads)
+		return false;
+	float cdf = normal_estimation(mx, 0.5, sum);
+	return 1 - cdf < error_percent;
+}
+
+// min_max[sum] = smallest max in [ceil(sum/2), sum] that passes, UINT32_MAX if none.
+// Verifies monotonicity exhaustively for sum <= 4096 and around the threshold otherwise.
+int build_ht_table(int min_reads, float error_percent, uint32_t n, uint32_t* out)
+{
+	for (uint32_t sum = 0; sum < n; ++sum) {
+		int lo = (int)((sum + 1) / 2), hi = (int)sum;
+		uint32_t thr = UINT32_MAX;
+		if (sum <= 4096) {
+			for (int m = lo; m <= hi; ++m) {
+				bool v = ht_valid(m, (int)sum, min_reads, error_percent);
+				if (v && thr == UINT32_MAX)
+					thr = (uint32_t)m;
+				if (!v && thr != UINT32_MAX)
+					return ARKS_E_NONMONOTONE;
+			}
+		} else {
+			if (ht_valid(hi, (int)sum, min_reads, error_percent)) {
+				int a = lo, b = hi; // invariant: b passes
+				while (a < b) {
+					int mid = a + (b - a) / 2;
+					if (ht_valid(mid, (int)sum, min_reads, error_percent))
+						b = mid;
+					else
+						a = mid + 1;
+				}
+				thr = (uint32_t)b;
+				for (int m = std::max(lo, b - 16); m < b; ++m)
+					if (ht_valid(m, (int)sum, min_reads, error_percent))
+						return ARKS_E_NONMONOTONE;
+				for (int m = b; m <= std::min(hi, b + 16); ++m)
+					if (!ht_valid(m, (int)sum, min_reads, error_percent))
+						return ARKS_E_NONMONOTONE;
+			}
+		}
+		out[sum] = thr;
+	}
+	return ARKS_OK;
+}
+
+int imap_alloc(arks_handle* h, uint64_t cap)
+{
+	CU(cudaMalloc(&h->imap, cap * 16));
+	// keys all-ones = empty; counters start at 0
+	init_slots_kernel<<<grid_for(h, cap * 2, 256, 8), 256, 0, h->stream>>>(h->imap, cap * 2, 2);
+	h->launches++;
+	CU(cudaGetLastError());
+	h->imap_cap = cap;
+	return ARKS_OK;
+}
+
+// make room for `incoming` more rows
+int imap_reserve(arks_handle* h, uint64_t incoming)
+{
+	if ((h->imap_upper + incoming) * 2 <= h->imap_cap) {
+		h->imap_upper += incoming;
+		return ARKS_OK;
+	}
+	unsigned long long actual = 0;
+	CU(cudaMemcpyAsync(&actual, h->d_imap_count, 8, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	h->imap_upper = actual;
+	if ((h->imap_upper + incoming) * 2 > h->imap_cap) {
+		uint64_t cap = h->imap_cap;
+		while ((h->imap_upper + incoming) * 4 > cap)
+			cap <<= 1;
+		unsigned long long* old = h->imap;
+		uint64_t old_cap = h->imap_cap;
+		int rc = imap_alloc(h, cap);
+		if (rc)
+			return rc;
+		CU(cudaMemsetAsync(h->d_imap_count, 0, 8, h->stream));
+		imap_rehash_kernel<<<grid_for(h, old_cap, 256, 8), 256, 0, h->stream>>>(old, old_cap, h->imap, cap - 1, h->d_imap_count);
+		h->launches++;
+		CU(cudaGetLastError());
+		CU(cudaStreamSynchronize(h->stream));
+		CU(cudaFree(old));
+	}
+	h->imap_upper += incoming;
+	return ARKS_OK;
+}
+
+int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const uint32_t* d_bc, uint32_t n_pairs, double j,
+    int32_t* d_out)
+{
+	MapParams P{};
+	P.table = h->table;
+	P.nslots = h->nslots;
+	P.k = (uint32_t)h->k;
+	P.mask_hi = h->mask_hi;
+	P.mask_lo = h->mask_lo;
+	P.j_index = j;
+	P.bases = d_bases;
+	P.read_off = d_off;
+	P.barcode_id = d_bc;
+	P.n_pairs = n_pairs;
+	P.conreci_out = d_out;
+	P.remap = h->d_remap;
+	P.n_remap = h->n_remap;
+	P.imap = h->imap;
+	P.imap_mask = h->imap_cap - 1;
+	P.imap_count = h->d_imap_count;
+	P.ctr = h->d_mctr;
+	int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_pairs + kMapWarps - 1) / kMapWarps, (uint64_t)h->map_grid));
+	if (h->kw == 1)
+		map_pairs_kernel<1><<<grid, kMapThreads, 0, h->stream>>>(P);
+	else
+		map_pairs_kernel<2><<<grid, kMapThreads, 0, h->stream>>>(P);
+	h->launches++;
+	CU(cudaGetLastError());
+	return ARKS_OK;
+}
+
+int run_index_add(arks_handle* h, const char* d_bases, const uint64_t* d_end_off, const uint32_t* d_conreci,
+    const uint64_t* h_end_off, uint32_t n_ends)
+{
+	const uint64_t n_bases = h_end_off[n_ends];
+	if (n_bases == 0)
+		return ARKS_OK;
+	const uint64_t n_words = (n_bases + 31) / 32 + 4;
+	int rc;
+	if ((rc = ensure(h, h->ib_inv, n_words * 4)))
+		return rc;
+	if ((rc = ensure(h, h->ib_skip, n_words * 4)))
+		return rc;
+	// tiles of kTileWindows windows
+	std::vector<IndexTile> tiles;
+	for (uint32_t e = 0; e < n_ends; ++e) {
+		uint64_t len = h_end_off[e + 1] - h_end_off[e];
+		if (len >= (uint64_t)h->k) {
+			if (len > 0xFFFFFFF0ull)
+				return fail(h, ARKS_E_ARG, "contig end longer than 4 Gbp");
+			uint32_t nwin = (uint32_t)(len - h->k + 1);
+			for (uint32_t s = 0; s < nwin; s += kTileWindows)
+				tiles.push_back(IndexTile{e, s});
+		}
+	}
+	if (tiles.empty())
+		return ARKS_OK;
+	if ((rc = ensure(h, h->ib_tiles, tiles.size() * sizeof(IndexTile))))
+		return rc;
+	CU(cudaMemcpyAsync(h->ib_tiles.p, tiles.data(), tiles.size() * sizeof(IndexTile), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemsetAsync(h->ib_skip.p, 0, n_words * 4, h->stream));
+	inv_mask_kernel<<<grid_for(h, (n_bases + 31) / 32, 256, 16), 256, 0, h->stream>>>(d_bases, n_bases, (uint32_t*)h->ib_inv.p);
+	walk_kernel<<<(n_ends + 127) / 128, 128, 0, h->stream>>>(d_end_off, n_ends, (uint32_t)h->k, (const uint32_t*)h->ib_inv.p,
+	    (uint32_t*)h->ib_skip.p, h->d_ictr);
+	int grid = (int)std::min<uint64_t>(tiles.size(), (uint64_t)h->sm_count * 8);
+	if (h->kw == 1)
+		insert_kernel<1><<<grid, kInsertThreads, 0, h->stream>>>((const IndexTile*)h->ib_tiles.p, (uint32_t)tiles.size(), d_bases,
+		    d_end_off, d_conreci, (const uint32_t*)h->ib_skip.p, h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo, h->d_ictr);
+	else
+		insert_kernel<2><<<grid, kInsertThreads, 0, h->stream>>>((const IndexTile*)h->ib_tiles.p, (uint32_t)tiles.size(), d_bases,
+		    d_end_off, d_conreci, (const uint32_t*)h->ib_skip.p, h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo, h->d_ictr);
+	h->launches += 3;
+	CU(cudaGetLastError());
+	// the tile vector is pageable host memory: wait for its copy before it goes out of scope
+	CU(cudaStreamSynchronize(h->stream));
+	return ARKS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
+{
+	arks_handle* h = nullptr;
+	if (!out)
+		return fail(nullptr, ARKS_E_ARG, "out is null");
+	*out = nullptr;
+	if (k < ARKS_MIN_K || k > ARKS_MAX_K)
+		return fail(nullptr, ARKS_E_ARG, "k must be in [4, 64]");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(nullptr, ARKS_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+	if (device < 0 || device >= ndev)
+		return fail(nullptr, ARKS_E_ARG, "bad device ordinal");
+	h = new arks_handle();
+	auto bail = [&](int code) {
+		std::string msg = h->err;
+		arks_destroy(h);
+		g_create_error = msg;
+		return code;
+	};
+#define CUC(call)                                                                        \
+	do {                                                                                 \
+		cudaError_t e_ = (call);                                                         \
+		if (e_ != cudaSuccess) {                                                         \
+			h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+			return bail(ARKS_E_CUDA);                                                    \
+		}                                                                                \
+	} while (0)
+	h->device = device;
+	h->k = k;
+	h->kw = k <= 32 ? 1 : 2;
+	key_masks(k, h->mask_hi, h->mask_lo);
+	CUC(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUC(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		h->err = "device is not sm_100 (Blackwell); this library contains sm_100a code only";
+		return bail(ARKS_E_CUDA);
+	}
+	h->sm_count = prop.multiProcessorCount;
+	CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+	CUC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+	h->stream = h->own_stream;
+	for (auto& s : h->slots) {
+		CUC(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+	}
+	double load = 0.5;
+	if (const char* s = getenv("ARKS_TABLE_LOAD")) {
+		double v = atof(s);
+		if (v > 0.05 && v < 0.95)
+			load = v;
+	}
+	h->nslots = std::max<uint64_t>(1024, (uint64_t)((double)max_kmers / load) + 1);
+	const size_t slot_bytes = h->kw == 1 ? 16 : 32;
+	CUC(cudaMalloc(&h->table, h->nslots * slot_bytes));
+	CUC(cudaMemsetAsync(h->table, 0xFF, h->nslots * slot_bytes, h->stream));
+	CUC(cudaMalloc(&h->d_ictr, sizeof(IndexCounters)));
+	CUC(cudaMemsetAsync(h->d_ictr, 0, sizeof(IndexCounters), h->stream));
+	CUC(cudaMalloc(&h->d_mctr, sizeof(MapCounters)));
+	CUC(cudaMemsetAsync(h->d_mctr, 0, sizeof(MapCounters), h->stream));
+	CUC(cudaMalloc(&h->d_imap_count, 8));
+	CUC(cudaMemsetAsync(h->d_imap_count, 0, 8, h->stream));
+	CUC(cudaMalloc(&h->d_pmap_count, 8));
+	CUC(cudaMalloc(&h->d_scratch, 64));
+	if (imap_alloc(h, 1ull << 16))
+		return bail(ARKS_E_CUDA);
+	int per_sm = 0;
+	if (h->kw == 1)
+		CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_pairs_kernel<1>, kMapThreads, 0));
+	else
+		CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_pairs_kernel<2>, kMapThreads, 0));
+	h->map_grid = h->sm_count * std::max(1, per_sm);
+	CUC(cudaStreamSynchronize(h->stream));
+#undef CUC
+	*out = h;
+	return ARKS_OK;
+}
+
+void arks_destroy(arks_handle* h)
+{
+	if (!h)
+		return;
+	cudaSetDevice(h->device);
+	if (h->stream)
+		cudaStreamSynchronize(h->stream);
+	if (h->copy_stream)
+		cudaStreamSynchronize(h->copy_stream);
+	for (DevBuf* b : {&h->ib_bases, &h->ib_off, &h->ib_conreci, &h->ib_inv, &h->ib_skip, &h->ib_tiles})
+		if (b->p)
+			cudaFree(b->p);
+	for (auto& s : h->slots) {
+		for (DevBuf* b : {&s.bases, &s.off, &s.bc, &s.out})
+			if (b->p)
+				cudaFree(b->p);
+		if (s.copied)
+			cudaEventDestroy(s.copied);
+		if (s.done)
+			cudaEventDestroy(s.done);
+	}
+	for (void* p : {(void*)h->table, (void*)h->d_ictr, (void*)h->d_mctr, (void*)h->d_remap, (void*)h->imap, (void*)h->d_imap_count,
+	         (void*)h->pmap, (void*)h->d_pmap_count, (void*)h->d_scratch})
+		if (p)
+			cudaFree(p);
+	if (h->own_stream)
+		cudaStreamDestroy(h->own_stream);
+	if (h->copy_stream)
+		cudaStreamDestroy(h->copy_stream);
+	delete h;
+}
+
+const char* arks_last_error(const arks_handle* h)
+{
+	return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int arks_set_stream(arks_handle* h, void* cuda_stream)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+	return ARKS_OK;
+}
+
+int arks_sync(arks_handle* h)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->copy_stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return ARKS_OK;
+}
+
+int arks_host_alloc(void** p, size_t bytes)
+{
+	arks_handle* h = nullptr;
+	if (!p)
+		return ARKS_E_ARG;
+	CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+	return ARKS_OK;
+}
+
+int arks_host_free(void* p)
+{
+	arks_handle* h = nullptr;
+	CU(cudaFreeHost(p));
+	return ARKS_OK;
+}
+
+uint64_t arks_launch_count(const arks_handle* h)
+{
+	return h ? h->launches : 0;
+}
+
+// ---- kernel 1 ----------------------------------------------------------------------------
+
+int arks_index_add(arks_handle* h, const char* bases, const uint64_t* end_off, const uint32_t* conreci, uint32_t n_ends)
+{
+	if (!h || !bases || !end_off || !conreci)
+		return fail(h, ARKS_E_ARG, "arks_index_add: null argument");
+	if (h->finalized)
+		return fail(h, ARKS_E_STATE, "arks_index_add after arks_index_finalize");
+	if (n_ends == 0)
+		return ARKS_OK;
+	CU(cudaSetDevice(h->device));
+	for (uint32_t e = 0; e < n_ends; ++e)
+		if (conreci[e] == 0 || conreci[e] >= 0x7FFFFFFFu || end_off[e + 1] < end_off[e])
+			return fail(h, ARKS_E_ARG, "arks_index_add: conreci must be >= 1 and offsets non-decreasing");
+	const uint64_t n_bases = end_off[n_ends] - end_off[0];
+	int rc;
+	if ((rc = ensure(h, h->ib_bases, n_bases + 64)) || (rc = ensure(h, h->ib_off, (n_ends + 1) * 8ull)) ||
+	    (rc = ensure(h, h->ib_conreci, n_ends * 4ull)))
+		return rc;
+	std::vector<uint64_t> rel(n_ends + 1);
+	for (uint32_t e = 0; e <= n_ends; ++e)
+		rel[e] = end_off[e] - end_off[0];
+	CU(cudaMemcpyAsync(h->ib_bases.p, bases + end_off[0], n_bases, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(h->ib_off.p, rel.data(), (n_ends + 1) * 8ull, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(h->ib_conreci.p, conreci, n_ends * 4ull, cudaMemcpyHostToDevice, h->stream));
+	rc = run_index_add(h, (const char*)h->ib_bases.p, (const uint64_t*)h->ib_off.p, (const uint32_t*)h->ib_conreci.p, rel.data(), n_ends);
+	if (rc)
+		return rc;
+	CU(cudaStreamSynchronize(h->stream));
+	return ARKS_OK;
+}
+
+int arks_index_add_device(arks_handle* h, const char* d_bases, const uint64_t* d_end_off, const uint32_t* d_conreci,
+    const uint64_t* h_end_off, uint32_t n_ends)
+{
+	if (!h || !d_bases || !d_end_off || !d_conreci || !h_end_off)
+		return fail(h, ARKS_E_ARG, "arks_index_add_device: null argument");
+	if (h->finalized)
+		return fail(h, ARKS_E_STATE, "arks_index_add after arks_index_finalize");
+	if (n_ends == 0)
+		return ARKS_OK;
+	if (h_end_off[0] != 0)
+		return fail(h, ARKS_E_ARG, "arks_index_add_device: end_off[0] must be 0");
+	CU(cudaSetDevice(h->device));
+	return run_index_add(h, d_bases, d_end_off, d_conreci, h_end_off, n_ends);
+}
+
+int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	if (!h->finalized) {
+		int grid = grid_for(h, h->nslots, 256, 16);
+		if (h->kw == 1)
+			finalize_kernel<1><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr);
+		else
+			finalize_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr);
+		h->launches++;
+		CU(cudaGetLastError());
+		IndexCounters c;
+		CU(cudaMemcpyAsync(&c, h->d_ictr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
+		if (c.probe_fail)
+			return fail(h, ARKS_E_CAPACITY, "index table full: more distinct k-mers than max_kmers allows");
+		h->istats.kmers_valid = c.kmers_valid;
+		h->istats.kmers_null = c.kmers_null;
+		h->istats.recorded = c.recorded;
+		h->istats.collisions = c.kmers_valid - c.recorded;
+		h->istats.removed = c.kmers_valid - c.sum_cmin;
+		h->istats.unique = c.unique;
+		h->finalized = true;
+	}
+	if (stats)
+		*stats = h->istats;
+	return ARKS_OK;
+}
+
+int arks_index_size(arks_handle* h, uint64_t* n_keys)
+{
+	if (!h || !n_keys)
+		return ARKS_E_ARG;
+	if (!h->finalized)
+		return fail(h, ARKS_E_STATE, "arks_index_size before arks_index_finalize");
+	*n_keys = h->istats.recorded;
+	return ARKS_OK;
+}
+
+int arks_index_dump(arks_handle* h, uint8_t* keys, int32_t* values, uint64_t cap, uint64_t* n_keys)
+{
+	if (!h || !keys || !values || !n_keys)
+		return ARKS_E_ARG;
+	if (!h->finalized)
+		return fail(h, ARKS_E_STATE, "arks_index_dump before arks_index_finalize");
+	CU(cudaSetDevice(h->device));
+	const uint64_t n = h->istats.recorded;
+	*n_keys = n;
+	if (cap < n)
+		return fail(h, ARKS_E_ARG, "arks_index_dump: cap too small");
+	if (n == 0)
+		return ARKS_OK;
+	uint64_t *d_hi = nullptr, *d_lo = nullptr;
+	int32_t* d_v = nullptr;
+	CU(cudaMalloc(&d_hi, n * 8));
+	CU(cudaMalloc(&d_lo, n * 8));
+	CU(cudaMalloc(&d_v, n * 4));
+	CU(cudaMemsetAsync(h->d_scratch, 0, 8, h->stream));
+	int grid = grid_for(h, h->nslots, 256, 16);
+	if (h->kw == 1)
+		dump_kernel<1><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, d_hi, d_lo, d_v, h->d_scratch, n);
+	else
+		dump_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, d_hi, d_lo, d_v, h->d_scratch, n);
+	h->launches++;
+	CU(cudaGetLastError());
+	std::vector<uint64_t> hi(n), lo(n);
+	CU(cudaMemcpyAsync(hi.data(), d_hi, n * 8, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaMemcpyAsync(lo.data(), d_lo, n * 8, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaMemcpyAsync(values, d_v, n * 4, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	cudaFree(d_hi);
+	cudaFree(d_lo);
+	cudaFree(d_v);
+	const int nb = (h->k + 3) / 4;
+	for (uint64_t i = 0; i < n; ++i)
+		for (int b = 0; b < nb; ++b)
+			keys[i * nb + b] = (uint8_t)(b < 8 ? hi[i] >> (56 - 8 * b) : lo[i] >> (56 - 8 * (b - 8)));
+	return ARKS_OK;
+}
+
+// ---- kernel 2 ----------------------------------------------------------------------------
+
+int arks_set_conreci_remap(arks_handle* h, const uint32_t* remap, uint32_t n)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	if (h->d_remap) {
+		CU(cudaFree(h->d_remap));
+		h->d_remap = nullptr;
+		h->n_remap = 0;
+	}
+	if (remap && n) {
+		for (uint32_t c = 1; c < n; ++c)
+			if (remap[c] == 0 || ((remap[c] ^ c) & 1u))
+				return fail(h, ARKS_E_ARG, "remap must keep head/tail parity and be >= 1");
+		CU(cudaMalloc(&h->d_remap, n * 4ull));
+		CU(cudaMemcpy(h->d_remap, remap, n * 4ull, cudaMemcpyHostToDevice));
+		h->n_remap = n;
+	}
+	return ARKS_OK;
+}
+
+int arks_map_pairs(arks_handle* h, const char* bases, const uint32_t* read_off, const uint32_t* barcode_id, uint32_t n_pairs,
+    double j_index, int32_t* conreci_out)
+{
+	if (!h || !bases || !read_off || !barcode_id)
+		return fail(h, ARKS_E_ARG, "arks_map_pairs: null argument");
+	if (!h->finalized)
+		return fail(h, ARKS_E_STATE, "arks_map_pairs before arks_index_finalize");
+	if (n_pairs == 0)
+		return ARKS_OK;
+	if (n_pairs > 0x7FFFFFFFu)
+		return fail(h, ARKS_E_ARG, "arks_map_pairs: at most 2^31-1 pairs per call");
+	CU(cudaSetDevice(h->device));
+	const uint32_t first = read_off[0];
+	const uint64_t n_bases = read_off[2ull * n_pairs] - first;
+	MapSlot& s = h->slots[h->next_slot];
+	h->next_slot ^= 1;
+	if (s.busy) { // the kernel that last read this slot's buffers must be finished
+		CU(cudaEventSynchronize(s.done));
+		s.busy = false;
+	}
+	int rc;
+	if ((rc = ensure(h, s.bases, n_bases + 64)) || (rc = ensure(h, s.off, (2ull * n_pairs + 1) * 4)) ||
+	    (rc = ensure(h, s.bc, n_pairs * 4ull)) || (conreci_out && (rc = ensure(h, s.out, n_pairs * 4ull))))
+		return rc;
+	if ((rc = imap_reserve(h, n_pairs)))
+		return rc;
+	CU(cudaMemcpyAsync(s.bases.p, bases + first, n_bases, cudaMemcpyHostToDevice, h->copy_stream));
+	CU(cudaMemcpyAsync(s.off.p, read_off, (2ull * n_pairs + 1) * 4, cudaMemcpyHostToDevice, h->copy_stream));
+	CU(cudaMemcpyAsync(s.bc.p, barcode_id, n_pairs * 4ull, cudaMemcpyHostToDevice, h->copy_stream));
+	CU(cudaEventRecord(s.copied, h->copy_stream));
+	CU(cudaStreamWaitEvent(h->stream, s.copied, 0));
+	// offsets are relative to read_off[0] on the device: bias the base pointer instead of rewriting them
+	const char* d_bases = (const char*)s.bases.p - first;
+	rc = launch_map(h, d_bases, (const uint32_t*)s.off.p, (const uint32_t*)s.bc.p, n_pairs, j_index,
+	    conreci_out ? (int32_t*)s.out.p : nullptr);
+	if (rc)
+		return rc;
+	if (conreci_out)
+		CU(cudaMemcpyAsync(conreci_out, s.out.p, n_pairs * 4ull, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaEventRecord(s.done, h->stream));
+	s.busy = true;
+	// inputs consumed once the copies have landed; the kernel keeps running
+	CU(cudaEventSynchronize(s.copied));
+	if (conreci_out)
+		CU(cudaStreamSynchronize(h->stream));
+	return ARKS_OK;
+}
+
+int arks_map_pairs_device(arks_handle* h, const char* d_bases, const uint32_t* d_read_off, const uint32_t* d_barcode_id,
+    uint32_t n_pairs, uint64_t n_bases, double j_index, int32_t* d_conreci_out)
+{
+	(void)n_bases;
+	if (!h || !d_bases || !d_read_off || !d_barcode_id)
+		return fail(h, ARKS_E_ARG, "arks_map_pairs_device: null argument");
+	if (!h->finalized)
+		return fail(h, ARKS_E_STATE, "arks_map_pairs before arks_index_finalize");
+	if (n_pairs == 0)
+		return ARKS_OK;
+	CU(cudaSetDevice(h->device));
+	int rc;
+	if ((rc = imap_reserve(h, n_pairs)))
+		return rc;
+	return launch_map(h, d_bases, d_read_off, d_barcode_id, n_pairs, j_index, d_conreci_out);
+}
+
+int arks_map_get_stats(arks_handle* h, arks_map_stats* stats)
+{
+	if (!h || !stats)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	MapCounters c;
+	CU(cudaMemcpyAsync(&c, h->d_mctr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	stats->kmers_valid = c.kmers_valid;
+	stats->kmers_invalid = c.kmers_invalid;
+	stats->found = c.found;
+	stats->recorded = c.recorded;
+	stats->dups = c.dups;
+	stats->reads_pass = c.reads_pass;
+	stats->reads_fail = c.reads_fail;
+	stats->pairs_stored = c.pairs_stored;
+	stats->pairs_invalid = c.pairs_invalid;
+	stats->pairs_nogood = c.pairs_nogood;
+	if (c.overflow)
+		return fail(h, ARKS_E_OVERFLOW, "a read hit more than 32 distinct contig ends; results for such reads are not exact");
+	return ARKS_OK;
+}
+
+int arks_map_stats_reset(arks_handle* h)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemsetAsync(h->d_mctr, 0, sizeof(MapCounters), h->stream));
+	return ARKS_OK;
+}
+
+// ---- imap / pmap -------------------------------------------------------------------------
+
+int arks_imap_size(arks_handle* h, uint64_t* n_rows)
+{
+	if (!h || !n_rows)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	unsigned long long n = 0;
+	CU(cudaMemcpyAsync(&n, h->d_imap_count, 8, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	*n_rows = n;
+	return ARKS_OK;
+}
+
+int arks_imap_export(arks_handle* h, uint32_t* barcode, uint32_t* contig, uint32_t* head, uint32_t* tail, uint64_t cap, uint64_t* n_rows)
+{
+	if (!h || !barcode || !contig || !head || !tail || !n_rows)
+		return ARKS_E_ARG;
+	int rc = arks_imap_size(h, n_rows);
+	if (rc)
+		return rc;
+	const uint64_t n = *n_rows;
+	if (cap < n)
+		return fail(h, ARKS_E_ARG, "arks_imap_export: cap too small");
+	if (n == 0)
+		return ARKS_OK;
+	uint32_t* d = nullptr;
+	CU(cudaMalloc(&d, n * 16));
+	CU(cudaMemsetAsync(h->d_scratch, 0, 8, h->stream));
+	imap_export_kernel<<<grid_for(h, h->imap_cap, 256, 8), 256, 0, h->stream>>>(h->imap, h->imap_cap, d, d + n, d + 2 * n, d + 3 * n,
+	    h->d_scratch, n);
+	h->launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(barcode, d, n * 4, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaMemcpyAsync(contig, d + n, n * 4, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaMemcpyAsync(head, d + 2 * n, n * 4, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaMemcpyAsync(tail, d + 3 * n, n * 4, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	cudaFree(d);
+	return ARKS_OK;
+}
+
+int arks_imap_add(arks_handle* h, const uint32_t* barcode, const uint32_t* contig, const uint32_t* head, const uint32_t* tail, uint64_t n_rows)
+{
+	if (!h || !barcode || !contig || !head || !tail)
+		return ARKS_E_ARG;
+	if (n_rows == 0)
+		return ARKS_OK;
+	CU(cudaSetDevice(h->device));
+	int rc;
+	if ((rc = imap_reserve(h, n_rows)))
+		return rc;
+	uint32_t* d = nullptr;
+	CU(cudaMalloc(&d, n_rows * 16));
+	CU(cudaMemcpyAsync(d, barcode, n_rows * 4, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(d + n_rows, contig, n_rows * 4, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(d + 2 * n_rows, head, n_rows * 4, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(d + 3 * n_rows, tail, n_rows * 4, cudaMemcpyHostToDevice, h->stream));
+	imap_add_rows_kernel<<<grid_for(h, n_rows, 256, 8), 256, 0, h->stream>>>(d, d + n_rows, d + 2 * n_rows, d + 3 * n_rows, n_rows,
+	    h->imap, h->imap_cap - 1, h->d_imap_count);
+	h->launches++;
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	cudaFree(d);
+	return ARKS_OK;
+}
+
+int arks_head_tail_table(int min_reads, float error_percent, uint32_t n, uint32_t* min_max)
+{
+	if (!min_max)
+		return ARKS_E_ARG;
+	return build_ht_table(min_reads, error_percent, n, min_max);
+}
+
+int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, int min_mult, int max_mult, int min_reads,
+    float error_percent, const uint32_t* lexrank, uint32_t n_contigs)
+{
+	if (!h || !mult || !lexrank)
+		return fail(h, ARKS_E_ARG, "arks_pair_links: null argument");
+	CU(cudaSetDevice(h->device));
+	h->pmap_ready = false;
+	h->pm_a.clear();
+	h->pm_b.clear();
+	h->pm_counts.clear();
+	cudaStream_t st = h->stream;
+	// 1. largest head+tail -> decision table
+	uint32_t* d_maxsum = reinterpret_cast<uint32_t*>(h->d_scratch);
+	CU(cudaMemsetAsync(h->d_scratch, 0, 64, st));
+	imap_maxsum_kernel<<<grid_for(h, h->imap_cap, 256, 8), 256, 0, st>>>(h->imap, h->imap_cap, d_maxsum);
+	h->launches++;
+	uint32_t maxsum = 0;
+	CU(cudaMemcpyAsync(&maxsum, d_maxsum, 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	std::vector<uint32_t> table(maxsum + 1);
+	int rc = build_ht_table(min_reads, error_percent, maxsum + 1, table.data());
+	if (rc)
+		return fail(h, rc, "head/tail predicate is not monotone in max for this (min_reads, error_percent)");
+	uint32_t *d_table = nullptr, *d_cnt = nullptr, *d_offs = nullptr, *d_fill = nullptr, *d_rows = nullptr, *d_sums = nullptr,
+	         *d_rank = nullptr;
+	int32_t* d_mult = nullptr;
+	auto cleanup = [&]() {
+		for (void* p : {(void*)d_table, (void*)d_cnt, (void*)d_offs, (void*)d_fill, (void*)d_rows, (void*)d_sums, (void*)d_rank, (void*)d_mult})
+			if (p)
+				cudaFree(p);
+	};
+#define CUL(call)                                                                            \
+	do {                                                                                     \
+		cudaError_t e_ = (call);                                                             \
+		if (e_ != cudaSuccess) {                                                             \
+			cleanup();                                                                       \
+			return fail(h, ARKS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+		}                                                                                    \
+	} while (0)
+	const uint32_t nb = std::max<uint32_t>(n_barcodes, 1);
+	const uint32_t n_scan_blocks = (nb + kScanBlock - 1) / kScanBlock;
+	CUL(cudaMalloc(&d_table, table.size() * 4));
+	CUL(cudaMalloc(&d_mult, nb * 4ull));
+	CUL(cudaMalloc(&d_cnt, nb * 4ull));
+	CUL(cudaMalloc(&d_fill, nb * 4ull));
+	CUL(cudaMalloc(&d_offs, (nb + 1) * 4ull));
+	CUL(cudaMalloc(&d_sums, n_scan_blocks * 4ull));
+	CUL(cudaMalloc(&d_rank, std::max<uint32_t>(n_contigs, 1) * 4ull));
+	CUL(cudaMemcpyAsync(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st));
+	CUL(cudaMemsetAsync(d_mult, 0, nb * 4ull, st));
+	if (n_barcodes)
+		CUL(cudaMemcpyAsync(d_mult, mult, n_barcodes * 4ull, cudaMemcpyHostToDevice, st));
+	if (n_contigs)
+		CUL(cudaMemcpyAsync(d_rank, lexrank, n_contigs * 4ull, cudaMemcpyHostToDevice, st));
+	CUL(cudaMemsetAsync(d_cnt, 0, nb * 4ull, st));
+	CUL(cudaMemsetAsync(d_fill, 0, nb * 4ull, st));
+	LinkParams L{h->imap, h->imap_cap, d_mult, n_barcodes, min_mult, max_mult, d_table, (uint32_t)table.size()};
+	const int g_imap = grid_for(h, h->imap_cap, 256, 8);
+	// 2. count passing rows per barcode, 3. scan, 4. scatter
+	imap_count_kernel<<<g_imap, 256, 0, st>>>(L, d_cnt);
+	scan_block_sums_kernel<<<n_scan_blocks, kScanBlock, 0, st>>>(d_cnt, nb, d_sums);
+	scan_sums_kernel<<<1, kScanBlock, 0, st>>>(d_sums, n_scan_blocks);
+	scan_apply_kernel<<<n_scan_blocks, kScanBlock, 0, st>>>(d_cnt, nb, d_sums, d_offs);
+	unsigned long long* d_events = h->d_scratch + 1;
+	pair_count_kernel<<<grid_for(h, nb, 256, 8), 256, 0, st>>>(d_cnt, nb, d_events);
+	h->launches += 5;
+	CUL(cudaGetLastError());
+	uint32_t n_rows = 0;
+	unsigned long long events = 0;
+	CUL(cudaMemcpyAsync(&n_rows, d_offs + nb, 4, cudaMemcpyDeviceToHost, st));
+	CUL(cudaMemcpyAsync(&events, d_events, 8, cudaMemcpyDeviceToHost, st));
+	CUL(cudaStreamSynchronize(st));
+	CUL(cudaMalloc(&d_rows, std::max<uint32_t>(n_rows, 1) * 4ull));
+	imap_scatter_kernel<<<g_imap, 256, 0, st>>>(L, d_offs, d_fill, d_rows);
+	h->launches++;
+	// 5. pmap table sized by the number of pair events (an upper bound on distinct pairs)
+	unsigned long long bound = events;
+	if (n_contigs) {
+		unsigned long long all = (unsigned long long)n_contigs * (n_contigs - 1) / 2;
+		bound = std::min(bound, all);
+	}
+	uint64_t cap = 1024;
+	while (cap < bound * 2)
+		cap <<= 1;
+	if (h->pmap) {
+		CUL(cudaFree(h->pmap));
+		h->pmap = nullptr;
+	}
+	CUL(cudaMalloc(&h->pmap, cap * 32));
+	h->pmap_cap = cap;
+	init_slots_kernel<<<grid_for(h, cap * 4, 256, 8), 256, 0, st>>>(h->pmap, cap * 4, 4);
+	h->launches++;
+	CUL(cudaMemsetAsync(h->d_pmap_count, 0, 8, st));
+	if (events) {
+		pair_kernel<<<grid_for(h, (uint64_t)nb * 32, 256, 8), 256, 0, st>>>(d_offs, d_rows, n_barcodes, d_rank, h->pmap, cap - 1, h->d_pmap_count);
+		h->launches++;
+	}
+	CUL(cudaGetLastError());
+	// 6. export + order by (rank a, rank b) = std::map<pair<string,string>> iteration order
+	unsigned long long n_pairs = 0;
+	CUL(cudaMemcpyAsync(&n_pairs, h->d_pmap_count, 8, cudaMemcpyDeviceToHost, st));
+	CUL(cudaStreamSynchronize(st));
+	if (n_pairs) {
+		uint32_t* d_out = nullptr;
+		CUL(cudaMalloc(&d_out, n_pairs * 24));
+		CUL(cudaMemsetAsync(h->d_scratch, 0, 8, st));
+		pmap_export_kernel<<<grid_for(h, cap, 256, 8), 256, 0, st>>>(h->pmap, cap, d_out, d_out + n_pairs, d_out + 2 * n_pairs, h->d_scratch, n_pairs);
+		h->launches++;
+		std::vector<uint32_t> a(n_pairs), b(n_pairs), c(4 * n_pairs);
+		cudaError_t e1 = cudaMemcpyAsync(a.data(), d_out, n_pairs * 4, cudaMemcpyDeviceToHost, st);
+		cudaError_t e2 = cudaMemcpyAsync(b.data(), d_out + n_pairs, n_pairs * 4, cudaMemcpyDeviceToHost, st);
+		cudaError_t e3 = cudaMemcpyAsync(c.data(), d_out + 2 * n_pairs, n_pairs * 16, cudaMemcpyDeviceToHost, st);
+		cudaError_t e4 = cudaStreamSynchronize(st);
+		cudaFree(d_out);
+		if (e1 || e2 || e3 || e4) {
+			cleanup();
+			return fail(h, ARKS_E_CUDA, "pmap export copy failed");
+		}
+		std::vector<uint64_t> order(n_pairs);
+		std::iota(order.begin(), order.end(), 0);
+		std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {
+			uint64_t kx = ((uint64_t)lexrank[a[x]] << 32) | lexrank[b[x]];
+			uint64_t ky = ((uint64_t)lexrank[a[y]] << 32) | lexrank[b[y]];
+			return kx < ky;
+		});
+		h->pm_a.resize(n_pairs);
+		h->pm_b.resize(n_pairs);
+		h->pm_counts.resize(4 * n_pairs);
+		for (uint64_t i = 0; i < n_pairs; ++i) {
+			h->pm_a[i] = a[order[i]];
+			h->pm_b[i] = b[order[i]];
+			memcpy(&h->pm_counts[4 * i], &c[4 * order[i]], 16);
+		}
+	}
+	cleanup();
+#undef CUL
+	h->pmap_ready = true;
+	return ARKS_OK;
+}
+
+int arks_pmap_size(arks_handle* h, uint64_t* n_rows)
+{
+	if (!h || !n_rows)
+		return ARKS_E_ARG;
+	if (!h->pmap_ready)
+		return fail(h, ARKS_E_STATE, "arks_pmap_size before arks_pair_links");
+	*n_rows = h->pm_a.size();
+	return ARKS_OK;
+}
+
+int arks_pmap_export(arks_handle* h, uint32_t* a, uint32_t* b, uint32_t* counts4, uint64_t cap, uint64_t* n_rows)
+{
+	if (!h || !a || !b || !counts4 || !n_rows)
+		return ARKS_E_ARG;
+	if (!h->pmap_ready)
+		return fail(h, ARKS_E_STATE, "arks_pmap_export before arks_pair_links");
+	const uint64_t n = h->pm_a.size();
+	*n_rows = n;
+	if (cap < n)
+		return fail(h, ARKS_E_ARG, "arks_pmap_export: cap too small");
+	if (n) {
+		memcpy(a, h->pm_a.data(), n * 4);
+		memcpy(b, h->pm_b.data(), n * 4);
+		memcpy(counts4, h->pm_counts.data(), n * 16);
+	}
+	return ARKS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,303 @@
+// arks_index.cuh -- kernel 1: contig-end k-merisation into the exact GPU hash table.
+//
+// Replaces mapKmers (Arcs/Arcs.cpp:869-929) + ReadsProcessor::prepSeq + the
+// google::sparse_hash_map / CityHash container (Arcs/Arcs.h:140-158).
+//
+// Per batch of contig ends (ASCII, concatenated):
+//   inv_mask_kernel   1 bit per base: not ACGTacgt                     (streaming)
+//   walk_kernel       one thread per end resolves mapKmers' sequential walk: a NULL
+//                     window at i jumps to i+k (:922-925), which can skip windows that
+//                     would have been valid; those are flagged in a skip bitmask and
+//                     the NULL events are counted.
+//   insert_kernel     one CTA per tile of 1024 windows: pack the tile's bases to 2 bits
+//                     in shared memory, every thread extracts canonical keys for its
+//                     windows and inserts them (128-bit CAS claim of the slot, then a
+//                     64-bit CAS on the slot's bookkeeping word).
+//   finalize_kernel   collapses bookkeeping into the final value per key + counters.
+//
+// Bookkeeping word w per key while building: (min conreci << 32) | multi-flag << 31 |
+// occurrences at that min conreci.  The reference's value rule (first conreci; any other
+// conreci -> 0, sticky; :903-920) is order independent: value = multi ? 0 : min conreci.
+// s_numkmersremdup counts, for ends processed in increasing conreci order (as
+// getContigKmers does), every occurrence of a key that is not in its smallest conreci,
+// so removed = sum over keys (total - count_at_min) = kmers_valid - sum count_at_min.
+#pragma once
+#include "arks_device.cuh"
+
+namespace arks {
+
+constexpr int kTileWindows = 1024;
+constexpr int kInsertThreads = 256;
+// words of packed region per tile: (1024 + 64 - 1 + 15)/16 = 68, +5 slack for extraction
+constexpr int kTileWords = 68 + 6;
+constexpr int kTileInvWords = 35 + 3;
+
+struct IndexCounters
+{
+	unsigned long long kmers_valid, kmers_null, recorded, unique, sum_cmin, probe_fail;
+};
+
+// ---- 1 bit per base: invalid --------------------------------------------------------
+__global__ void inv_mask_kernel(const char* __restrict__ bases, uint64_t n_bases, uint32_t* __restrict__ inv)
+{
+	uint64_t n_words = (n_bases + 31) / 32;
+	for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t b0 = w * 32;
+		uint32_t remain = (uint32_t)min((uint64_t)32, n_bases - b0);
+		uint32_t m = 0;
+#pragma unroll
+		for (int g = 0; g < 2; ++g) {
+			if (remain > 16u * g) {
+				uint32_t inv16, nn, no;
+				pack_group(bases + b0 + 16 * g, remain - 16 * g, 0, &inv16, &nn, &no);
+				m |= inv16 << (16 * g);
+			}
+		}
+		inv[w] = m;
+	}
+}
+
+// first set bit of the LSB-first bitmask in [from, to), or `to`
+__device__ __forceinline__ uint64_t next_set_bit(const uint32_t* mask, uint64_t from, uint64_t to)
+{
+	if (from >= to)
+		return to;
+	uint64_t w = from >> 5;
+	uint32_t cur = mask[w] & (0xFFFFFFFFu << (from & 31));
+	uint64_t wend = (to - 1) >> 5;
+	while (true) {
+		if (cur) {
+			uint64_t pos = (w << 5) + (uint64_t)(__ffs(cur) - 1);
+			return pos < to ? pos : to;
+		}
+		if (w == wend)
+			return to;
+		cur = mask[++w];
+	}
+}
+
+// ---- mapKmers' walk (Arcs.cpp:886-927) -------------------------------------------------
+__global__ void walk_kernel(const uint64_t* __restrict__ end_off, uint32_t n_ends, uint32_t k,
+    const uint32_t* __restrict__ inv, uint32_t* __restrict__ skip, IndexCounters* ctr)
+{
+	uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long nnull = 0;
+	if (e < n_ends) {
+		uint64_t s = end_off[e], t = end_off[e + 1];
+		uint64_t len = t - s;
+		if (len >= k) {
+			uint64_t last = len - k; // last window start
+			uint64_t i = 0;
+			while (i <= last) {
+				uint64_t q = next_set_bit(inv, s + i, t) - s;
+				if (q >= len)
+					break; // every remaining window is valid
+				uint64_t ip = (q + 1 >= k && q + 1 - k > i) ? q + 1 - k : i; // first NULL window reached
+				if (ip > last)
+					break;
+				nnull++;
+				// the jump skips windows [ip, ip+k); flag them (those containing q are NULL anyway)
+				uint64_t a = s + ip, b = min(s + ip + k, s + last + 1);
+				for (uint64_t w = a >> 5; w <= (b - 1) >> 5; ++w) {
+					uint64_t lo = max(a, w << 5), hi = min(b, (w + 1) << 5);
+					uint32_t m = (hi - lo) >= 32 ? 0xFFFFFFFFu : (((1u << (hi - lo)) - 1u) << (lo & 31));
+					atomicOr(&skip[w], m);
+				}
+				i = ip + k;
+			}
+		}
+	}
+	nnull = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)nnull); // per-thread counts are small
+	if ((threadIdx.x & 31) == 0 && nnull)
+		atomicAdd(&ctr->kmers_null, nnull);
+}
+
+// ---- insert --------------------------------------------------------------------------
+__device__ __forceinline__ void
+cas128(uint64_t* p, uint64_t c_lo, uint64_t c_hi, uint64_t n_lo, uint64_t n_hi, uint64_t& o_lo, uint64_t& o_hi)
+{
+	asm volatile("{\n\t.reg .b128 c, n, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+	             "atom.global.cas.b128 d, [%6], c, n;\n\tmov.b128 {%0, %1}, d;\n\t}"
+	             : "=l"(o_lo), "=l"(o_hi)
+	             : "l"(c_lo), "l"(c_hi), "l"(n_lo), "l"(n_hi), "l"(p)
+	             : "memory");
+}
+
+// Finds or claims the slot of `key`; returns the address of its bookkeeping word, or
+// nullptr if the table is full.
+template <int KW>
+__device__ __forceinline__ unsigned long long* find_or_claim(uint8_t* table, uint64_t nslots, const Key128& key)
+{
+	uint64_t slot = hash_to_slot(key_hash<KW>(key), nslots);
+	for (uint64_t probes = 0; probes < nslots; ++probes) {
+		if (KW == 1) {
+			unsigned long long* p = reinterpret_cast<unsigned long long*>(table + slot * 16);
+			unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(p);
+			if (cur == kEmptyKey)
+				cur = atomicCAS(p, (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
+			if (cur == kEmptyKey || cur == key.hi)
+				return p + 1;
+		} else {
+			uint64_t* p = reinterpret_cast<uint64_t*>(table + slot * 32);
+			uint64_t hi, lo;
+			asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(hi), "=l"(lo) : "l"(p));
+			if (hi == kEmptyKey && lo == kEmptyKey) {
+				// memory order of the pair is (p[0], p[1]) = (hi, lo); b128 = {low 64, high 64}
+				cas128(p, kEmptyKey, kEmptyKey, key.hi, key.lo, hi, lo);
+				if (hi == kEmptyKey && lo == kEmptyKey)
+					return reinterpret_cast<unsigned long long*>(p + 2);
+			}
+			if (hi == key.hi && lo == key.lo)
+				return reinterpret_cast<unsigned long long*>(p + 2);
+		}
+		slot = slot + 1 == nslots ? 0 : slot + 1;
+	}
+	return nullptr;
+}
+
+__device__ __forceinline__ void note_occurrence(unsigned long long* wp, uint32_t conreci)
+{
+	unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(wp);
+	while (true) {
+		unsigned long long nw;
+		if (old == kEmptyW) {
+			nw = ((unsigned long long)conreci << 32) | 1ull;
+		} else {
+			uint32_t mc = (uint32_t)(old >> 32);
+			if (conreci < mc)
+				nw = ((unsigned long long)conreci << 32) | kMultiFlag | 1ull;
+			else if (conreci == mc)
+				nw = old + 1ull;
+			else
+				nw = old | kMultiFlag;
+		}
+		if (nw == old)
+			return;
+		unsigned long long prev = atomicCAS(wp, old, nw);
+		if (prev == old)
+			return;
+		old = prev;
+	}
+}
+
+struct IndexTile
+{
+	uint32_t end;    // index of the contig end in this batch
+	uint32_t start;  // first window of the tile within the end
+};
+
+template <int KW>
+__global__ void __launch_bounds__(kInsertThreads)
+insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char* __restrict__ bases,
+    const uint64_t* __restrict__ end_off, const uint32_t* __restrict__ conreci, const uint32_t* __restrict__ skip,
+    uint8_t* table, uint64_t nslots, uint32_t k, uint64_t mask_hi, uint64_t mask_lo, IndexCounters* ctr)
+{
+	__shared__ uint32_t W[kTileWords];
+	__shared__ uint32_t RC[kTileWords];
+	__shared__ uint32_t INV[kTileInvWords];
+	__shared__ uint32_t inv16s[kTileWords];
+	unsigned long long my_valid = 0;
+	bool fail = false;
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		IndexTile tl = tiles[tile];
+		uint64_t s = end_off[tl.end];
+		uint32_t len = (uint32_t)(end_off[tl.end + 1] - s);
+		uint32_t nwin_total = len - k + 1;
+		uint32_t nw = min((uint32_t)kTileWindows, nwin_total - tl.start);
+		uint32_t Lc = nw + k - 1;
+		uint32_t nwords = (Lc + 15) >> 4;
+		const char* src = bases + s + tl.start;
+		for (uint32_t g = threadIdx.x; g < nwords; g += blockDim.x) {
+			uint32_t inv16, nn, no;
+			W[g] = pack_group(src, Lc, g, &inv16, &nn, &no);
+			inv16s[g] = inv16;
+		}
+		__syncthreads();
+		for (uint32_t g = threadIdx.x; g < nwords; g += blockDim.x)
+			RC[g] = rev2(~W[nwords - 1 - g]);
+		for (uint32_t m = threadIdx.x; m < (nwords + 1) / 2; m += blockDim.x)
+			INV[m] = inv16s[2 * m] | ((2 * m + 1 < nwords ? inv16s[2 * m + 1] : 0u) << 16);
+		__syncthreads();
+		uint32_t cr = conreci[tl.end];
+		uint64_t gpos0 = s + tl.start;
+		for (uint32_t p = threadIdx.x; p < nw; p += blockDim.x) {
+			uint64_t gp = gpos0 + p;
+			bool skipped = (skip[gp >> 5] >> (gp & 31)) & 1u;
+			if (skipped || window_invalid(INV, p, k))
+				continue;
+			Key128 key = canonical_key<KW>(W, RC, p, k, nwords * 16, mask_hi, mask_lo);
+			unsigned long long* wp = find_or_claim<KW>(table, nslots, key);
+			if (wp == nullptr) {
+				fail = true;
+				continue;
+			}
+			note_occurrence(wp, cr);
+			my_valid++;
+		}
+		__syncthreads();
+	}
+	uint32_t v = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)my_valid);
+	if ((threadIdx.x & 31) == 0 && v)
+		atomicAdd(&ctr->kmers_valid, (unsigned long long)v);
+	if (fail)
+		atomicAdd(&ctr->probe_fail, 1ull);
+}
+
+// ---- finalize ------------------------------------------------------------------------
+// Slots touched since the last finalize carry a bookkeeping word with a non-zero high
+// half (conreci >= 1); finalized slots carry (0 << 32) | value.  Re-finalising is a no-op.
+template <int KW>
+__global__ void finalize_kernel(uint8_t* table, uint64_t nslots, IndexCounters* ctr)
+{
+	unsigned long long rec = 0, uniq = 0, cmin = 0;
+	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t* p = reinterpret_cast<uint64_t*>(table + sidx * SlotBytes<KW>::value);
+		bool empty = KW == 1 ? (p[0] == kEmptyKey) : (p[0] == kEmptyKey && p[1] == kEmptyKey);
+		if (empty)
+			continue;
+		uint64_t w = p[KW];
+		if ((w >> 32) == 0)
+			continue; // already final
+		uint32_t mc = (uint32_t)(w >> 32);
+		bool multi = (w & kMultiFlag) != 0;
+		p[KW] = multi ? 0ull : (uint64_t)mc;
+		rec++;
+		uniq += multi ? 0 : 1;
+		cmin += (uint32_t)w & 0x7FFFFFFFu;
+	}
+	// block reduce through warp sums
+	for (int o = 16; o > 0; o >>= 1) {
+		rec += __shfl_down_sync(0xFFFFFFFFu, rec, o);
+		uniq += __shfl_down_sync(0xFFFFFFFFu, uniq, o);
+		cmin += __shfl_down_sync(0xFFFFFFFFu, cmin, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (rec)
+			atomicAdd(&ctr->recorded, rec);
+		if (uniq)
+			atomicAdd(&ctr->unique, uniq);
+		if (cmin)
+			atomicAdd(&ctr->sum_cmin, cmin);
+	}
+}
+
+// copies (key, value) of every occupied slot to dense arrays (for tests / dumps)
+template <int KW>
+__global__ void dump_kernel(const uint8_t* table, uint64_t nslots, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* vals,
+    unsigned long long* counter, uint64_t cap)
+{
+	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t* p = reinterpret_cast<const uint64_t*>(table + sidx * SlotBytes<KW>::value);
+		bool empty = KW == 1 ? (p[0] == kEmptyKey) : (p[0] == kEmptyKey && p[1] == kEmptyKey);
+		if (empty)
+			continue;
+		unsigned long long i = atomicAdd(counter, 1ull);
+		if (i < cap) {
+			keys_hi[i] = p[0];
+			keys_lo[i] = KW == 2 ? p[1] : 0ull;
+			vals[i] = (int32_t)(uint32_t)p[KW];
+		}
+	}
+}
+
+} // namespace arks

@@ -1,0 +1,217 @@
+"""GPU parity: the CUDA path (through the C ABI of libarks_b200.so) against the CPU
+restatement (oracle/) on the same seeded inputs -- bit-exact for every integer result --
+and against the reference's golden demo outputs."""
+import os
+
+import numpy as np
+import pytest
+
+import glue
+import oracle_lib as O
+import seqio
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _arks():
+    import arcs_b200
+    return arcs_b200
+
+
+def _sorted_rows(keys, vals):
+    if len(vals) == 0:
+        return keys, vals
+    order = np.lexsort(keys.T[::-1])
+    return keys[order], vals[order]
+
+
+def _oracle_index(k, bases, end_off, conreci):
+    km = O.KMap(k, int(end_off[-1]))
+    for e in range(len(conreci)):
+        km.map_kmers(bases[int(end_off[e]):int(end_off[e + 1])].tobytes(), int(conreci[e]))
+    return km
+
+
+def _check_index(k, bases, end_off, conreci, split=None):
+    A = _arks()
+    km = _oracle_index(k, bases, end_off, conreci)
+    idx = A.ArksIndex(k, int(end_off[-1]) + 16)
+    if split:  # several add calls
+        for a in range(0, len(conreci), split):
+            b = min(len(conreci), a + split)
+            idx.add_ends(bases, end_off[a:b + 1], conreci[a:b])
+    else:
+        idx.add_ends(bases, end_off, conreci)
+    st = idx.finalize().as_dict()
+    ref = km.stats.as_dict()
+    assert st == ref, (st, ref)
+    gk, gv = _sorted_rows(*idx.dump())
+    ok, ov = km.dump()
+    assert gk.shape == ok.shape
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(gv, ov)
+    return idx, km
+
+
+@pytest.mark.parametrize("k", [4, 5, 8, 16, 20, 21, 30, 31, 32, 33, 40, 47, 60, 63, 64])
+def test_index_build_matches_oracle(k):
+    rng = np.random.default_rng(100 + k)
+    genome, contigs = synth.make_draft(rng, 60000, 4000, k, n_runs=12, palindromes=6, iupac=6)
+    bases, end_off, conreci, _ = synth.contig_end_arrays(genome, contigs, k, min_size=500, end_length=1500)
+    _check_index(k, bases, end_off, conreci, split=None if k % 2 else 5)
+
+
+def test_index_edge_cases():
+    k = 20
+    seqs = [
+        b"ACGT" * 3,  # shorter than k: ignored
+        b"A" * 19,
+        b"ACGTTGCATGCATGCATGCA",  # exactly one window
+        b"N" * 50,
+        b"ACGTACGTAC" * 5 + b"N" + b"TTGACCAGTA" * 5,
+        b"GATTACAGATTACAGATTACAN",  # N in the last position
+        b"NGATTACAGATTACAGATTACA",
+        b"AT" * 40,  # palindromes everywhere
+        b"CG" * 40,
+        b"acgtnACGT" * 20,
+        b"ACGTTGCATGCATGCATGCA",  # duplicate of an earlier end -> value 0
+        b"TGCATGCATGCATGCAACGT",  # its reverse complement
+        b"ACGTTGCATGCATGCATGCANNACGTTGCATGCATGCATGCATTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT",  # NN: jump skips valid windows
+        b"",
+    ]
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    end_off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    end_off[1:] = np.cumsum([len(s) for s in seqs])
+    conreci = np.arange(1, len(seqs) + 1, dtype=np.uint32)
+    _check_index(k, bases, end_off, conreci)
+
+
+def _check_map(k, j, genome, contigs, rng, **read_kw):
+    bases, end_off, conreci, names = synth.contig_end_arrays(genome, contigs, k, min_size=500, end_length=3000)
+    idx, km = _check_index(k, bases, end_off, conreci)
+    rb, roff, bc = synth.make_reads(rng, genome, **read_kw)
+    got = idx.map_pairs(rb, roff, bc, j)
+    want, st = km.map_pairs(rb, roff, j)
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+    assert idx.map_stats().as_dict() == st.as_dict()
+    return idx, km, names, bc, got
+
+
+@pytest.mark.parametrize("k,j", [(20, 0.05), (30, 0.55), (32, 0.3), (33, 0.3), (40, 0.5), (60, 0.55), (64, 0.2)])
+def test_map_pairs_matches_oracle(k, j):
+    rng = np.random.default_rng(7 * k)
+    genome, contigs = synth.make_draft(rng, 120000, 8000, k, n_runs=10, palindromes=4)
+    _check_map(k, j, genome, contigs, rng, n_barcodes=40, pairs_per_barcode=30, read_len=150, mol_len=20000,
+               mols_per_barcode=2, sub_rate=0.004, n_rate=0.002, len_jitter=40)
+
+
+def test_map_pairs_ragged_and_long_reads():
+    k, j = 24, 0.1
+    rng = np.random.default_rng(5)
+    genome, contigs = synth.make_draft(rng, 80000, 9000, k)
+    bases, end_off, conreci, _ = synth.contig_end_arrays(genome, contigs, k, end_length=4000)
+    idx, km = _check_index(k, bases, end_off, conreci)
+    reads = []
+    for L in [0, 1, k - 1, k, k + 1, 100, 511, 512, 513, 700, 1024, 2500, 150, 150]:
+        p = int(rng.integers(0, len(genome) - L - 1))
+        r = genome[p:p + L].copy()
+        reads.append(r)
+    reads.append(np.frombuffer(b"ACGTNNNNNNNNACGT" * 10, dtype=np.uint8))  # too many N
+    reads.append(genome[100:250].copy())
+    bad = genome[300:450].copy()
+    bad[7] = ord("R")  # non-ACGTN character: invalid pair
+    reads.append(bad)
+    reads.append(genome[300:450].copy())
+    assert len(reads) % 2 == 0
+    rb = np.concatenate(reads)
+    roff = np.zeros(len(reads) + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(r) for r in reads])
+    bc = np.arange(len(reads) // 2, dtype=np.uint32)
+    got = idx.map_pairs(rb, roff, bc, j)
+    want, st = km.map_pairs(rb, roff, j)
+    assert np.array_equal(got, want)
+    assert idx.map_stats().as_dict() == st.as_dict()
+
+
+def test_pair_links_match_oracle():
+    k, j = 30, 0.4
+    rng = np.random.default_rng(11)
+    genome, contigs = synth.make_draft(rng, 300000, 6000, k)
+    idx, km, names, bc, conreci = _check_map(k, j, genome, contigs, rng, n_barcodes=150, pairs_per_barcode=60,
+                                            mol_len=30000, mols_per_barcode=3)
+    # imap parity
+    barcodes = [str(b) for b in bc]
+    imap, uniq = glue.imap_rows(barcodes, conreci, names)
+    gb, gc, gh, gt = idx.imap()
+    got_rows = sorted(zip(gb.tolist(), gc.tolist(), gh.tolist(), gt.tolist()))
+    want_rows = sorted((int(b), c, ht[0], ht[1]) for b, d in imap.items() for c, ht in d.items())
+    assert got_rows == want_rows
+    # pmap parity for a few parameter sets
+    rank = glue.lex_rank(uniq)
+    nb = int(bc.max()) + 1
+    mult = np.bincount(bc, minlength=nb).astype(np.int32) * 2
+    rows = np.array(want_rows, dtype=np.uint32)
+    for (c, r, mlo, mhi) in [(5, 0.05, 50, 10000), (2, 0.2, 1, 100000), (3, 0.01, 120, 121), (1, 0.5, 0, 10 ** 6)]:
+        a, b, counts = idx.pair_links(mult, mlo, mhi, c, r, rank)
+        oa, ob, oc = O.pair_contigs(rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], mult, mlo, mhi, c, np.float32(r), rank)
+        assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(counts, oc)
+        assert glue.gv_text(a, b, counts, uniq, rank, 0, np.float32(r)) == glue.gv_text(oa, ob, oc, uniq, rank, 0, np.float32(r))
+
+
+def _gpu_demo(fa, fq, k, j, c, m, e, z, r, l, multfile=None):
+    A = _arks()
+    contigs = seqio.read_fasta(fa)
+    ends, names = glue.contig_ends(contigs, z, e)
+    bases = np.frombuffer(b"".join(s for s, _ in ends), dtype=np.uint8)
+    end_off = np.zeros(len(ends) + 1, dtype=np.uint64)
+    end_off[1:] = np.cumsum([len(s) for s, _ in ends])
+    conreci = np.array([cr for _, cr in ends], dtype=np.uint32)
+    idx = A.ArksIndex(k, int(end_off[-1]))
+    idx.add_ends(bases, end_off, conreci)
+    ist = idx.finalize().as_dict()
+    recs = seqio.read_fastq(fq)
+    if multfile:
+        mult = {ln.split()[0]: int(ln.split()[1]) for ln in open(multfile)}
+    else:
+        mult = seqio.multiplicities(recs)
+    barcodes, rb, roff = seqio.candidate_pairs(recs, mult)
+    bnames = sorted(set(barcodes))
+    bid = {b: i for i, b in enumerate(bnames)}
+    bc = np.array([bid[b] for b in barcodes], dtype=np.uint32)
+    # feed in several batches, as the host pipeline does
+    n = len(bc)
+    step = max(1, n // 3)
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        idx.map_pairs(rb, roff[2 * a:2 * b + 1], bc[a:b], j, want_conreci=False)
+    mst = idx.map_stats().as_dict()
+    ids, uniq = glue.name_ids(names)
+    rank = glue.lex_rank(uniq)
+    multv = np.array([mult.get(b, 0) for b in bnames], dtype=np.int32)
+    a, b, counts = idx.pair_links(multv, m[0], m[1], c, r, rank)
+    return ist, mst, glue.gv_text(a, b, counts, uniq, rank, l, np.float32(r)), idx
+
+
+def test_arks_demo_golden_gpu():
+    d = os.path.join(GOLD, "arks_demo")
+    ist, mst, gv, idx = _gpu_demo(os.path.join(d, "test_scaffolds.renamed.fa"), os.path.join(d, "test_reads.fq.gz"),
+                                  k=30, j=0.55, c=5, m=(50, 6000), e=30000, z=500, r=0.05, l=0)
+    assert gv == open(os.path.join(d, "expected_original.gv")).read()
+    assert (ist["kmers_valid"], ist["kmers_null"], ist["recorded"], ist["collisions"], ist["removed"], ist["unique"]) == (
+        123190, 303, 118710, 4480, 547, 118334)
+    assert (mst["pairs_stored"], mst["pairs_invalid"], mst["pairs_nogood"]) == (21632, 0, 6012)
+    assert (mst["kmers_valid"], mst["kmers_invalid"], mst["found"], mst["recorded"], mst["dups"]) == (
+        6109324, 0, 4862376, 4814099, 48277)
+    assert (mst["reads_pass"], mst["reads_fail"]) == (44503, 10785)
+    assert idx.launches > 0
+
+
+def test_arks_long_demo_golden_gpu():
+    d = os.path.join(GOLD, "arks_long_demo")
+    _, _, gv, _ = _gpu_demo(os.path.join(d, "test_scaffolds.renamed.fa"), os.path.join(d, "test_reads.cut250.fq.gz"),
+                            k=20, j=0.05, c=3, m=(8, 10000), e=30000, z=500, r=0.05, l=0,
+                            multfile=os.path.join(d, "barcodeMultiplicityArcs.tsv"))
+    assert gv == open(os.path.join(d, "expected_original.gv")).read()
