@@ -50,14 +50,27 @@ struct arks_handle
 	bool finalized = false;
 	IndexCounters* d_ictr = nullptr;
 	arks_index_stats istats{};
-	DevBuf ib_bases, ib_off, ib_conreci, ib_inv, ib_skip, ib_tiles;
+	DevBuf ib_bases, ib_off, ib_conreci, ib_inv, ib_skip, ib_tiles, ib_g0;
+	// persistent packed contig text (seed-and-extend), global base coordinates
+	DevBuf ct_T, ct_TINS, ct_TUNIQ, ct_end_g0, ct_end_len, ct_end_cr;
+	uint64_t g_next = 0;      // next free base coordinate (multiple of 32)
+	uint32_t n_global_ends = 0;
+	int use_extension = 1;
+	// exact integer thresholds for the Jaccard gate and the N-fraction test
+	uint32_t* d_jmin = nullptr;
+	uint32_t* d_nmax = nullptr;
+	double jmin_for = 0.0;
+	bool jmin_valid = false;
 	// map
 	MapCounters* d_mctr = nullptr;
 	MapSlot slots[2];
 	int next_slot = 0;
 	uint32_t* d_remap = nullptr;
 	uint32_t n_remap = 0;
-	int map_grid = 0;
+	int map_grid = 0, group_grid = 0, slow_grid = 0;
+	DevBuf worklist, mate_state; // scratch of one map launch (launches on a handle are stream-ordered)
+	uint32_t* d_work_count = nullptr;
+	int map_mode_pair = 0;
 	// imap
 	unsigned long long* imap = nullptr;
 	uint64_t imap_cap = 0;
@@ -107,6 +120,38 @@ int ensure(arks_handle* h, DevBuf& b, size_t bytes)
 	CU(cudaMalloc(&b.p, want));
 	b.cap = want;
 	return ARKS_OK;
+}
+
+// grows a persistent buffer, keeping its contents; the new tail is zero-filled
+int grow_keep(arks_handle* h, DevBuf& b, size_t bytes)
+{
+	if (b.cap >= bytes && b.p)
+		return ARKS_OK;
+	size_t want = bytes + bytes / 2 + 4096;
+	void* np = nullptr;
+	CU(cudaMalloc(&np, want));
+	CU(cudaMemsetAsync(np, 0, want, h->stream));
+	if (b.p) {
+		CU(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
+		CU(cudaFree(b.p));
+	}
+	b.p = np;
+	b.cap = want;
+	return ARKS_OK;
+}
+
+ContigText contig_text(const arks_handle* h)
+{
+	ContigText ct;
+	ct.T = (uint32_t*)h->ct_T.p;
+	ct.TINS = (uint32_t*)h->ct_TINS.p;
+	ct.TUNIQ = (uint32_t*)h->ct_TUNIQ.p;
+	ct.end_g0 = (const uint64_t*)h->ct_end_g0.p;
+	ct.end_len = (const uint32_t*)h->ct_end_len.p;
+	ct.end_cr = (const uint32_t*)h->ct_end_cr.p;
+	ct.n_bases = h->g_next;
+	return ct;
 }
 
 int grid_for(const arks_handle* h, uint64_t work_items, int block, int per_sm)
@@ -227,10 +272,34 @@ int imap_reserve(arks_handle* h, uint64_t incoming)
 	return ARKS_OK;
 }
 
+// jmin[total] = smallest count with (double)count / (double)total > j  (bestContig, Arcs.cpp:997-1006)
+int update_jmin(arks_handle* h, double j)
+{
+	if (h->jmin_valid && h->jmin_for == j)
+		return ARKS_OK;
+	std::vector<uint32_t> t(kRegionBases + 1, UINT32_MAX);
+	for (int total = 1; total <= kRegionBases; ++total)
+		for (int c = 1; c <= total; ++c)
+			if ((double)c / (double)total > j) {
+				t[total] = (uint32_t)c;
+				break;
+			}
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaMemcpy(h->d_jmin, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+	h->jmin_for = j;
+	h->jmin_valid = true;
+	return ARKS_OK;
+}
+
 int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const uint32_t* d_bc, uint32_t n_pairs, double j,
     int32_t* d_out)
 {
+	int rcj = update_jmin(h, j);
+	if (rcj)
+		return rcj;
 	MapParams P{};
+	P.jmin = h->d_jmin;
+	P.nmax = h->d_nmax;
 	P.table = h->table;
 	P.nslots = h->nslots;
 	P.k = (uint32_t)h->k;
@@ -248,11 +317,41 @@ int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const
 	P.imap_mask = h->imap_cap - 1;
 	P.imap_count = h->d_imap_count;
 	P.ctr = h->d_mctr;
-	int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_pairs + kMapWarps - 1) / kMapWarps, (uint64_t)h->map_grid));
-	if (h->kw == 1)
-		map_pairs_kernel<1><<<grid, kMapThreads, 0, h->stream>>>(P);
-	else
-		map_pairs_kernel<2><<<grid, kMapThreads, 0, h->stream>>>(P);
+	P.ct_T = (const uint32_t*)h->ct_T.p;
+	P.ct_TINS = (const uint32_t*)h->ct_TINS.p;
+	P.ct_TUNIQ = (const uint32_t*)h->ct_TUNIQ.p;
+	P.ct_end_g0 = (const uint64_t*)h->ct_end_g0.p;
+	P.ct_end_len = (const uint32_t*)h->ct_end_len.p;
+	P.ct_end_cr = (const uint32_t*)h->ct_end_cr.p;
+	P.ct_n_bases = h->g_next;
+	P.use_extension = h->use_extension && h->ct_T.p != nullptr;
+	if (h->map_mode_pair) {
+		int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_pairs + kMapWarps - 1) / kMapWarps, (uint64_t)h->map_grid));
+		if (h->kw == 1)
+			map_pairs_kernel<1><<<grid, kMapThreads, 0, h->stream>>>(P);
+		else
+			map_pairs_kernel<2><<<grid, kMapThreads, 0, h->stream>>>(P);
+	} else {
+		int rcw;
+		if ((rcw = ensure(h, h->worklist, n_pairs * 4ull)) || (rcw = ensure(h, h->mate_state, n_pairs * 8ull)))
+			return rcw;
+		P.worklist = (uint32_t*)h->worklist.p;
+		P.mate_state = (uint32_t*)h->mate_state.p;
+		P.work_count = h->d_work_count;
+		CU(cudaMemsetAsync(h->d_work_count, 0, 4, h->stream));
+		const uint64_t groups = ((uint64_t)n_pairs + kGroupPairs - 1) / kGroupPairs;
+		int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + kGroupWarps - 1) / kGroupWarps, (uint64_t)h->group_grid));
+		const size_t smem = sizeof(GroupSmem) * kGroupWarps;
+		int sgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_pairs + kMapWarps - 1) / kMapWarps, (uint64_t)h->slow_grid));
+		if (h->kw == 1) {
+			map_groups_kernel<1><<<grid, kGroupThreads, smem, h->stream>>>(P);
+			map_slow_kernel<1><<<sgrid, kMapThreads, 0, h->stream>>>(P);
+		} else {
+			map_groups_kernel<2><<<grid, kGroupThreads, smem, h->stream>>>(P);
+			map_slow_kernel<2><<<sgrid, kMapThreads, 0, h->stream>>>(P);
+		}
+		h->launches++;
+	}
 	h->launches++;
 	CU(cudaGetLastError());
 	return ARKS_OK;
@@ -282,8 +381,34 @@ int run_index_add(arks_handle* h, const char* d_bases, const uint64_t* d_end_off
 				tiles.push_back(IndexTile{e, s});
 		}
 	}
-	if (tiles.empty())
+	// global coordinates of this batch's ends in the persistent packed text (each end starts
+	// at a multiple of 32 bases) and the per-end metadata
+	std::vector<uint64_t> g0(n_ends);
+	std::vector<uint32_t> elen(n_ends);
+	uint64_t g = h->g_next;
+	for (uint32_t e = 0; e < n_ends; ++e) {
+		g0[e] = g;
+		elen[e] = (uint32_t)(h_end_off[e + 1] - h_end_off[e]);
+		g = (g + elen[e] + 31) & ~31ull;
+	}
+	if (g >= (1ull << kPosBits) || (uint64_t)h->n_global_ends + n_ends >= (1ull << 24))
+		return fail(h, ARKS_E_ARG, "contig text too large for the slot position field");
+	const uint32_t first_end = h->n_global_ends;
+	if ((rc = grow_keep(h, h->ct_T, (g / 16 + 8) * 4)) || (rc = grow_keep(h, h->ct_TINS, (g / 32 + 8) * 4)) ||
+	    (rc = grow_keep(h, h->ct_TUNIQ, (g / 32 + 8) * 4)) || (rc = grow_keep(h, h->ct_end_g0, ((uint64_t)first_end + n_ends) * 8)) ||
+	    (rc = grow_keep(h, h->ct_end_len, ((uint64_t)first_end + n_ends) * 4)) ||
+	    (rc = grow_keep(h, h->ct_end_cr, ((uint64_t)first_end + n_ends) * 4)) || (rc = ensure(h, h->ib_g0, n_ends * 8ull)))
+		return rc;
+	CU(cudaMemcpyAsync(h->ib_g0.p, g0.data(), n_ends * 8ull, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync((uint64_t*)h->ct_end_g0.p + first_end, g0.data(), n_ends * 8ull, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync((uint32_t*)h->ct_end_len.p + first_end, elen.data(), n_ends * 4ull, cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync((uint32_t*)h->ct_end_cr.p + first_end, d_conreci, n_ends * 4ull, cudaMemcpyDeviceToDevice, h->stream));
+	h->g_next = g;
+	h->n_global_ends += n_ends;
+	if (tiles.empty()) {
+		CU(cudaStreamSynchronize(h->stream));
 		return ARKS_OK;
+	}
 	if ((rc = ensure(h, h->ib_tiles, tiles.size() * sizeof(IndexTile))))
 		return rc;
 	CU(cudaMemcpyAsync(h->ib_tiles.p, tiles.data(), tiles.size() * sizeof(IndexTile), cudaMemcpyHostToDevice, h->stream));
@@ -294,10 +419,12 @@ int run_index_add(arks_handle* h, const char* d_bases, const uint64_t* d_end_off
 	int grid = (int)std::min<uint64_t>(tiles.size(), (uint64_t)h->sm_count * 8);
 	if (h->kw == 1)
 		insert_kernel<1><<<grid, kInsertThreads, 0, h->stream>>>((const IndexTile*)h->ib_tiles.p, (uint32_t)tiles.size(), d_bases,
-		    d_end_off, d_conreci, (const uint32_t*)h->ib_skip.p, h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo, h->d_ictr);
+		    d_end_off, d_conreci, (const uint32_t*)h->ib_skip.p, (const uint64_t*)h->ib_g0.p, first_end, contig_text(h), h->table,
+		    h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo, h->d_ictr);
 	else
 		insert_kernel<2><<<grid, kInsertThreads, 0, h->stream>>>((const IndexTile*)h->ib_tiles.p, (uint32_t)tiles.size(), d_bases,
-		    d_end_off, d_conreci, (const uint32_t*)h->ib_skip.p, h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo, h->d_ictr);
+		    d_end_off, d_conreci, (const uint32_t*)h->ib_skip.p, (const uint64_t*)h->ib_g0.p, first_end, contig_text(h), h->table,
+		    h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo, h->d_ictr);
 	h->launches += 3;
 	CU(cudaGetLastError());
 	// the tile vector is pageable host memory: wait for its copy before it goes out of scope
@@ -350,6 +477,8 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		return bail(ARKS_E_CUDA);
 	}
 	h->sm_count = prop.multiProcessorCount;
+	if (const char* s = getenv("ARKS_STACK"))
+		CUC(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(s)));
 	CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
 	CUC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	h->stream = h->own_stream;
@@ -364,7 +493,9 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 			load = v;
 	}
 	h->nslots = std::max<uint64_t>(1024, (uint64_t)((double)max_kmers / load) + 1);
-	const size_t slot_bytes = h->kw == 1 ? 16 : 32;
+	const size_t slot_bytes = kSlotBytes;
+	if (const char* s = getenv("ARKS_NO_EXTEND"))
+		h->use_extension = atoi(s) ? 0 : 1;
 	CUC(cudaMalloc(&h->table, h->nslots * slot_bytes));
 	CUC(cudaMemsetAsync(h->table, 0xFF, h->nslots * slot_bytes, h->stream));
 	CUC(cudaMalloc(&h->d_ictr, sizeof(IndexCounters)));
@@ -377,12 +508,47 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 	CUC(cudaMalloc(&h->d_scratch, 64));
 	if (imap_alloc(h, 1ull << 16))
 		return bail(ARKS_E_CUDA);
+	{
+		// nmax[len] = largest N count with !((double)n / (double)len > 0.02)  (checkReadSequence, Arcs.cpp:383-386)
+		std::vector<uint32_t> t(kRegionBases + 1, 0);
+		for (int len = 1; len <= kRegionBases; ++len)
+			for (int n = 0; n <= len; ++n) {
+				double ar = (double)n / (double)len;
+				if (ar > 0.02)
+					break;
+				t[len] = (uint32_t)n;
+			}
+		CUC(cudaMalloc(&h->d_jmin, (kRegionBases + 1) * 4));
+		CUC(cudaMalloc(&h->d_nmax, (kRegionBases + 1) * 4));
+		CUC(cudaMemcpy(h->d_nmax, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+	}
 	int per_sm = 0;
 	if (h->kw == 1)
 		CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_pairs_kernel<1>, kMapThreads, 0));
 	else
 		CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_pairs_kernel<2>, kMapThreads, 0));
 	h->map_grid = h->sm_count * std::max(1, per_sm);
+	{
+		const size_t smem = sizeof(GroupSmem) * kGroupWarps;
+		int per_sm_g = 0;
+		if (h->kw == 1) {
+			CUC(cudaFuncSetAttribute(map_groups_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, map_groups_kernel<1>, kGroupThreads, smem));
+		} else {
+			CUC(cudaFuncSetAttribute(map_groups_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, map_groups_kernel<2>, kGroupThreads, smem));
+		}
+		h->group_grid = h->sm_count * std::max(1, per_sm_g);
+		int per_sm_s = 0;
+		if (h->kw == 1)
+			CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, map_slow_kernel<1>, kMapThreads, 0));
+		else
+			CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, map_slow_kernel<2>, kMapThreads, 0));
+		h->slow_grid = h->sm_count * std::max(1, per_sm_s);
+		CUC(cudaMalloc(&h->d_work_count, 4));
+		if (const char* s = getenv("ARKS_MAP_MODE"))
+			h->map_mode_pair = strcmp(s, "pair") == 0;
+	}
 	CUC(cudaStreamSynchronize(h->stream));
 #undef CUC
 	*out = h;
@@ -398,7 +564,8 @@ void arks_destroy(arks_handle* h)
 		cudaStreamSynchronize(h->stream);
 	if (h->copy_stream)
 		cudaStreamSynchronize(h->copy_stream);
-	for (DevBuf* b : {&h->ib_bases, &h->ib_off, &h->ib_conreci, &h->ib_inv, &h->ib_skip, &h->ib_tiles})
+	for (DevBuf* b : {&h->ib_bases, &h->ib_off, &h->ib_conreci, &h->ib_inv, &h->ib_skip, &h->ib_tiles, &h->ib_g0, &h->ct_T, &h->ct_TINS,
+	         &h->ct_TUNIQ, &h->ct_end_g0, &h->ct_end_len, &h->ct_end_cr})
 		if (b->p)
 			cudaFree(b->p);
 	for (auto& s : h->slots) {
@@ -411,7 +578,8 @@ void arks_destroy(arks_handle* h)
 			cudaEventDestroy(s.done);
 	}
 	for (void* p : {(void*)h->table, (void*)h->d_ictr, (void*)h->d_mctr, (void*)h->d_remap, (void*)h->imap, (void*)h->d_imap_count,
-	         (void*)h->pmap, (void*)h->d_pmap_count, (void*)h->d_scratch})
+	         (void*)h->pmap, (void*)h->d_pmap_count, (void*)h->d_scratch, (void*)h->d_jmin, (void*)h->d_nmax, (void*)h->d_work_count,
+	         h->worklist.p, h->mate_state.p})
 		if (p)
 			cudaFree(p);
 	if (h->own_stream)
@@ -459,6 +627,15 @@ int arks_host_free(void* p)
 {
 	arks_handle* h = nullptr;
 	CU(cudaFreeHost(p));
+	return ARKS_OK;
+}
+
+// debugging aid (not in the public header): copies internal scratch to the host
+int arks_debug_copy(arks_handle* h, int what, void* dst, size_t bytes)
+{
+	const void* src = what == 0 ? (const void*)h->d_work_count : what == 1 ? h->worklist.p : h->mate_state.p;
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
 	return ARKS_OK;
 }
 
@@ -527,6 +704,15 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 			finalize_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr);
 		h->launches++;
 		CU(cudaGetLastError());
+		if (h->g_next && h->ct_T.p) {
+			int g2 = grid_for(h, (h->g_next + 31) / 32 * 32, 256, 8);
+			if (h->kw == 1)
+				uniq_mask_kernel<1><<<g2, 256, 0, h->stream>>>(contig_text(h), h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo);
+			else
+				uniq_mask_kernel<2><<<g2, 256, 0, h->stream>>>(contig_text(h), h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo);
+			h->launches++;
+			CU(cudaGetLastError());
+		}
 		IndexCounters c;
 		CU(cudaMemcpyAsync(&c, h->d_ictr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
 		CU(cudaStreamSynchronize(h->stream));

@@ -205,12 +205,15 @@ __device__ __noinline__ Key128 palindrome_key(const Key128& f, int k)
 // (Lp - k - p) of RC).
 template <int KW>
 __device__ __forceinline__ Key128
-canonical_key(const uint32_t* W, const uint32_t* RC, uint32_t p, uint32_t k, uint32_t Lp, uint64_t mask_hi, uint64_t mask_lo)
+canonical_key(const uint32_t* W, const uint32_t* RC, uint32_t p, uint32_t k, uint32_t Lp, uint64_t mask_hi, uint64_t mask_lo,
+    bool* fwd_is_canonical = nullptr)
 {
 	Key128 f = extract_window<KW>(W, p, mask_hi, mask_lo);
 	Key128 r = extract_window<KW>(RC, Lp - k - p, mask_hi, mask_lo);
 	bool f_less = (f.hi < r.hi) || (f.hi == r.hi && f.lo < r.lo);
 	bool equal = (f.hi == r.hi) && (f.lo == r.lo);
+	if (fwd_is_canonical)
+		*fwd_is_canonical = f_less || equal;
 	if (equal)
 		return palindrome_key(f, (int)k);
 	return f_less ? f : r;
@@ -235,38 +238,79 @@ __device__ __forceinline__ uint64_t hash_to_slot(uint64_t h, uint64_t nslots)
 	return __umul64hi(h, nslots);
 }
 
-// Table slot: KW=1 -> 16 B {key, w};  KW=2 -> 32 B {hi, lo, w, pad}.  After finalize the
-// low 32 bits of w hold the value (contig-end record, 0 = several ends).
-template <int KW>
-struct SlotBytes
-{
-	static constexpr int value = KW == 1 ? 16 : 32;
-};
-
-// One probe of the frozen table: returns true if the slot decides the lookup
-// (found -> *val set, or empty -> *val = kMiss), false if probing must continue.
+// Table slot, 32 B (one DRAM sector) for every k:
+//   [0]  key.hi          [8]  key.lo (unused, left all-ones, when k <= 32)
+//   [16] w               build time: bookkeeping word; frozen: low 32 bits = value
+//                        (contig-end record, 0 = seen in several ends), high 32 bits = 0
+//   [24] posinfo         where the claiming occurrence sits in the packed contig text:
+//                        bits 0-38 global base coordinate of the window, bit 39 = canonical
+//                        key is the forward strand of the contig, bits 40-63 = global index
+//                        of the contig end
+constexpr int kSlotBytes = 32;
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
+constexpr int kPosBits = 39;
+constexpr uint64_t kPosMask = (1ull << kPosBits) - 1ull;
+
+__device__ __forceinline__ void
+load_slot(const uint8_t* table, uint64_t slot, uint64_t& hi, uint64_t& lo, uint32_t& val, uint64_t& posinfo)
+{
+	const uint8_t* p = table + slot * kSlotBytes;
+	uint64_t a, b, c, d;
+	asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+	hi = a;
+	lo = b;
+	val = (uint32_t)c;
+	posinfo = d;
+}
 
 template <int KW>
-__device__ __forceinline__ void load_slot(const uint8_t* table, uint64_t slot, uint64_t& hi, uint64_t& lo, uint32_t& val)
+__device__ __forceinline__ bool slot_matches(uint64_t hi, uint64_t lo, const Key128& key)
 {
+	return hi == key.hi && (KW == 1 || lo == key.lo);
+}
+
+template <int KW>
+__device__ __forceinline__ bool slot_empty(uint64_t hi, uint64_t lo)
+{
+	return hi == kEmptyKey && (KW == 1 || lo == kEmptyKey);
+}
+
+// reverse the 32 two-bit groups of a 64-bit word
+__device__ __forceinline__ uint64_t rev2_64(uint64_t x)
+{
+	return ((uint64_t)rev2((uint32_t)x) << 32) | rev2((uint32_t)(x >> 32));
+}
+
+// reverse complement of a left-aligned packed k-mer (same result as reading the
+// reverse-complement stream)
+template <int KW>
+__device__ __forceinline__ Key128 revcomp_key(const Key128& f, uint32_t k)
+{
+	Key128 r;
 	if (KW == 1) {
-		const uint8_t* p = table + slot * 16;
-		uint64_t a, b;
-		asm("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-		hi = a;
-		lo = 0;
-		val = (uint32_t)b;
+		uint64_t a = rev2_64(~f.hi); // pad bases (complemented to T) lead: shift them out
+		r.hi = a << (2 * (32 - k));
+		r.lo = 0;
 	} else {
-		const uint8_t* p = table + slot * 32;
-		uint64_t a, b, c, d;
-		asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-		             : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
-		             : "l"(p));
-		hi = a;
-		lo = b;
-		val = (uint32_t)c;
+		uint64_t a = rev2_64(~f.lo), b = rev2_64(~f.hi); // (a:b) = revcomp of the 64-base padded string
+		uint32_t s = 2 * (64 - k);                        // 0 .. 62
+		r.hi = s ? (a << s) | (b >> (64 - s)) : a;
+		r.lo = b << s;
 	}
+	return r;
+}
+
+// canonical key from the forward packing alone
+template <int KW>
+__device__ __forceinline__ Key128 canonical_from_forward(const Key128& f, uint32_t k, bool* fwd_is_canonical)
+{
+	Key128 r = revcomp_key<KW>(f, k);
+	bool f_less = (f.hi < r.hi) || (f.hi == r.hi && f.lo < r.lo);
+	bool equal = (f.hi == r.hi) && (f.lo == r.lo);
+	*fwd_is_canonical = f_less || equal;
+	if (equal)
+		return palindrome_key(f, (int)k);
+	return f_less ? f : r;
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)

@@ -123,32 +123,40 @@ cas128(uint64_t* p, uint64_t c_lo, uint64_t c_hi, uint64_t n_lo, uint64_t n_hi, 
 	             : "memory");
 }
 
-// Finds or claims the slot of `key`; returns the address of its bookkeeping word, or
-// nullptr if the table is full.
+// Finds or claims the slot of `key`; returns the slot's base address (nullptr if the table
+// is full) and whether this call claimed it.
 template <int KW>
-__device__ __forceinline__ unsigned long long* find_or_claim(uint8_t* table, uint64_t nslots, const Key128& key)
+__device__ __forceinline__ uint64_t* find_or_claim(uint8_t* table, uint64_t nslots, const Key128& key, bool* claimed)
 {
 	uint64_t slot = hash_to_slot(key_hash<KW>(key), nslots);
+	*claimed = false;
 	for (uint64_t probes = 0; probes < nslots; ++probes) {
+		uint64_t* p = reinterpret_cast<uint64_t*>(table + slot * kSlotBytes);
 		if (KW == 1) {
-			unsigned long long* p = reinterpret_cast<unsigned long long*>(table + slot * 16);
-			unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(p);
-			if (cur == kEmptyKey)
-				cur = atomicCAS(p, (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
-			if (cur == kEmptyKey || cur == key.hi)
-				return p + 1;
+			unsigned long long* pk = reinterpret_cast<unsigned long long*>(p);
+			unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(pk);
+			if (cur == kEmptyKey) {
+				cur = atomicCAS(pk, (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
+				if (cur == kEmptyKey) {
+					*claimed = true;
+					return p;
+				}
+			}
+			if (cur == key.hi)
+				return p;
 		} else {
-			uint64_t* p = reinterpret_cast<uint64_t*>(table + slot * 32);
 			uint64_t hi, lo;
 			asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(hi), "=l"(lo) : "l"(p));
 			if (hi == kEmptyKey && lo == kEmptyKey) {
 				// memory order of the pair is (p[0], p[1]) = (hi, lo); b128 = {low 64, high 64}
 				cas128(p, kEmptyKey, kEmptyKey, key.hi, key.lo, hi, lo);
-				if (hi == kEmptyKey && lo == kEmptyKey)
-					return reinterpret_cast<unsigned long long*>(p + 2);
+				if (hi == kEmptyKey && lo == kEmptyKey) {
+					*claimed = true;
+					return p;
+				}
 			}
 			if (hi == key.hi && lo == key.lo)
-				return reinterpret_cast<unsigned long long*>(p + 2);
+				return p;
 		}
 		slot = slot + 1 == nslots ? 0 : slot + 1;
 	}
@@ -183,14 +191,29 @@ __device__ __forceinline__ void note_occurrence(unsigned long long* wp, uint32_t
 struct IndexTile
 {
 	uint32_t end;    // index of the contig end in this batch
-	uint32_t start;  // first window of the tile within the end
+	uint32_t start;  // first window of the tile within the end (multiple of kTileWindows)
+};
+
+// Persistent packed copy of every contig end (global base coordinates; every end starts at a
+// multiple of 32): T = 2-bit text, 16 bases per word, MSB first; TINS bit g = the window
+// starting at g was inserted by mapKmers' walk; TUNIQ bit g = its key maps to one contig end.
+struct ContigText
+{
+	uint32_t* T;
+	uint32_t* TINS;
+	uint32_t* TUNIQ;
+	const uint64_t* end_g0;   // per global end index
+	const uint32_t* end_len;
+	const uint32_t* end_cr;
+	uint64_t n_bases;         // coordinates in use
 };
 
 template <int KW>
 __global__ void __launch_bounds__(kInsertThreads)
 insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char* __restrict__ bases,
     const uint64_t* __restrict__ end_off, const uint32_t* __restrict__ conreci, const uint32_t* __restrict__ skip,
-    uint8_t* table, uint64_t nslots, uint32_t k, uint64_t mask_hi, uint64_t mask_lo, IndexCounters* ctr)
+    const uint64_t* __restrict__ batch_g0, uint32_t first_global_end, ContigText ct, uint8_t* table, uint64_t nslots, uint32_t k,
+    uint64_t mask_hi, uint64_t mask_lo, IndexCounters* ctr)
 {
 	__shared__ uint32_t W[kTileWords];
 	__shared__ uint32_t RC[kTileWords];
@@ -206,11 +229,17 @@ insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char*
 		uint32_t nw = min((uint32_t)kTileWindows, nwin_total - tl.start);
 		uint32_t Lc = nw + k - 1;
 		uint32_t nwords = (Lc + 15) >> 4;
+		const bool last_tile = tl.start + nw == nwin_total;
 		const char* src = bases + s + tl.start;
+		const uint64_t g0 = batch_g0[tl.end] + tl.start; // global coordinate of the tile's first base (multiple of 32)
 		for (uint32_t g = threadIdx.x; g < nwords; g += blockDim.x) {
 			uint32_t inv16, nn, no;
-			W[g] = pack_group(src, Lc, g, &inv16, &nn, &no);
+			uint32_t w = pack_group(src, Lc, g, &inv16, &nn, &no);
+			W[g] = w;
 			inv16s[g] = inv16;
+			// persistent text: a tile owns its first kTileWindows bases; the end's last tile owns the rest
+			if (last_tile || g < (uint32_t)kTileWindows / 16)
+				ct.T[(g0 >> 4) + g] = w;
 		}
 		__syncthreads();
 		for (uint32_t g = threadIdx.x; g < nwords; g += blockDim.x)
@@ -218,21 +247,35 @@ insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char*
 		for (uint32_t m = threadIdx.x; m < (nwords + 1) / 2; m += blockDim.x)
 			INV[m] = inv16s[2 * m] | ((2 * m + 1 < nwords ? inv16s[2 * m + 1] : 0u) << 16);
 		__syncthreads();
-		uint32_t cr = conreci[tl.end];
-		uint64_t gpos0 = s + tl.start;
-		for (uint32_t p = threadIdx.x; p < nw; p += blockDim.x) {
-			uint64_t gp = gpos0 + p;
-			bool skipped = (skip[gp >> 5] >> (gp & 31)) & 1u;
-			if (skipped || window_invalid(INV, p, k))
-				continue;
-			Key128 key = canonical_key<KW>(W, RC, p, k, nwords * 16, mask_hi, mask_lo);
-			unsigned long long* wp = find_or_claim<KW>(table, nslots, key);
-			if (wp == nullptr) {
-				fail = true;
-				continue;
+		const uint32_t cr = conreci[tl.end];
+		const uint64_t gpos0 = s + tl.start;
+		const uint64_t end_tag = (uint64_t)(first_global_end + tl.end) << 40;
+		for (uint32_t pb = 0; pb < nw; pb += blockDim.x) { // warp-uniform trip count
+			const uint32_t p = pb + threadIdx.x;
+			bool inserted = false;
+			if (p < nw) {
+				const uint64_t gp = gpos0 + p;
+				const bool skipped = (skip[gp >> 5] >> (gp & 31)) & 1u;
+				if (!skipped && !window_invalid(INV, p, k)) {
+					bool fwd_canon;
+					Key128 key = canonical_key<KW>(W, RC, p, k, nwords * 16, mask_hi, mask_lo, &fwd_canon);
+					bool claimed;
+					uint64_t* sp = find_or_claim<KW>(table, nslots, key, &claimed);
+					if (sp == nullptr) {
+						fail = true;
+					} else {
+						if (claimed)
+							sp[3] = end_tag | ((uint64_t)fwd_canon << kPosBits) | (g0 + p);
+						note_occurrence(reinterpret_cast<unsigned long long*>(sp + 2), cr);
+						my_valid++;
+						inserted = true;
+					}
+				}
 			}
-			note_occurrence(wp, cr);
-			my_valid++;
+			// 32 consecutive windows of one warp = one word of the inserted-window mask
+			const uint32_t word = __ballot_sync(0xFFFFFFFFu, inserted);
+			if ((threadIdx.x & 31) == 0 && pb + (threadIdx.x & ~31u) < nw)
+				ct.TINS[(g0 + pb + threadIdx.x) >> 5] = word;
 		}
 		__syncthreads();
 	}
@@ -251,16 +294,15 @@ __global__ void finalize_kernel(uint8_t* table, uint64_t nslots, IndexCounters* 
 {
 	unsigned long long rec = 0, uniq = 0, cmin = 0;
 	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
-		uint64_t* p = reinterpret_cast<uint64_t*>(table + sidx * SlotBytes<KW>::value);
-		bool empty = KW == 1 ? (p[0] == kEmptyKey) : (p[0] == kEmptyKey && p[1] == kEmptyKey);
-		if (empty)
+		uint64_t* p = reinterpret_cast<uint64_t*>(table + sidx * kSlotBytes);
+		if (slot_empty<KW>(p[0], p[1]))
 			continue;
-		uint64_t w = p[KW];
+		uint64_t w = p[2];
 		if ((w >> 32) == 0)
 			continue; // already final
 		uint32_t mc = (uint32_t)(w >> 32);
 		bool multi = (w & kMultiFlag) != 0;
-		p[KW] = multi ? 0ull : (uint64_t)mc;
+		p[2] = multi ? 0ull : (uint64_t)mc;
 		rec++;
 		uniq += multi ? 0 : 1;
 		cmin += (uint32_t)w & 0x7FFFFFFFu;
@@ -281,21 +323,62 @@ __global__ void finalize_kernel(uint8_t* table, uint64_t nslots, IndexCounters* 
 	}
 }
 
+// frozen-table lookup of one key: value, or kMiss
+template <int KW>
+__device__ __forceinline__ uint32_t lookup_value(const uint8_t* table, uint64_t nslots, const Key128& key)
+{
+	uint64_t slot = hash_to_slot(key_hash<KW>(key), nslots);
+	while (true) {
+		uint64_t hi, lo, posinfo;
+		uint32_t val;
+		load_slot(table, slot, hi, lo, val, posinfo);
+		if (slot_matches<KW>(hi, lo, key))
+			return val;
+		if (slot_empty<KW>(hi, lo))
+			return kMiss;
+		slot = slot + 1 == nslots ? 0 : slot + 1;
+	}
+}
+
+// TUNIQ bit g = the key of the inserted window at g maps to exactly one contig end
+template <int KW>
+__global__ void uniq_mask_kernel(ContigText ct, const uint8_t* table, uint64_t nslots, uint32_t k, uint64_t mask_hi, uint64_t mask_lo)
+{
+	const uint64_t n_words = (ct.n_bases + 31) >> 5;
+	const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	for (uint64_t w = warp0; w < n_words; w += nwarps) {
+		const uint32_t ins = ct.TINS[w];
+		bool uq = false;
+		if ((ins >> lane) & 1u) {
+			const uint64_t g = (w << 5) + lane;
+			Key128 f = extract_window<KW>(ct.T + (g >> 4), (uint32_t)(g & 15), mask_hi, mask_lo);
+			bool fc;
+			Key128 key = canonical_from_forward<KW>(f, k, &fc);
+			uint32_t v = lookup_value<KW>(table, nslots, key);
+			uq = v != 0 && v != kMiss;
+		}
+		const uint32_t word = __ballot_sync(0xFFFFFFFFu, uq);
+		if (lane == 0)
+			ct.TUNIQ[w] = word;
+	}
+}
+
 // copies (key, value) of every occupied slot to dense arrays (for tests / dumps)
 template <int KW>
 __global__ void dump_kernel(const uint8_t* table, uint64_t nslots, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* vals,
     unsigned long long* counter, uint64_t cap)
 {
 	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
-		const uint64_t* p = reinterpret_cast<const uint64_t*>(table + sidx * SlotBytes<KW>::value);
-		bool empty = KW == 1 ? (p[0] == kEmptyKey) : (p[0] == kEmptyKey && p[1] == kEmptyKey);
-		if (empty)
+		const uint64_t* p = reinterpret_cast<const uint64_t*>(table + sidx * kSlotBytes);
+		if (slot_empty<KW>(p[0], p[1]))
 			continue;
 		unsigned long long i = atomicAdd(counter, 1ull);
 		if (i < cap) {
 			keys_hi[i] = p[0];
 			keys_lo[i] = KW == 2 ? p[1] : 0ull;
-			vals[i] = (int32_t)(uint32_t)p[KW];
+			vals[i] = (int32_t)(uint32_t)p[2];
 		}
 	}
 }

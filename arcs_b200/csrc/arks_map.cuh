@@ -9,11 +9,16 @@
 // then owns independent windows: it extracts the canonical key with funnel shifts
 // (no rolling state), hashes it and probes the frozen table with one 16/32-byte
 // non-allocating load.  Four probes per lane are in flight before the first is
-// consumed.  Per-read votes live in registers, one tracked contig end per lane; the
+// consumed.  Because a random probe costs a whole 128-byte DRAM line on this chip
+// (profiles/r01_probe_microbench.txt), only a few seed windows per mate are probed first;
+// a seed hit locates the read in the packed contig text and every window that matches the
+// text exactly is resolved by comparison (seed-and-extend) -- the remaining windows are
+// probed.  Per-read votes live in registers, one tracked contig end per lane; the
 // argmax (ties -> smallest contig end, as std::map iteration with a strict '<' gives,
 // :996-1004) and the Jaccard gate (IEEE double division, :1006) finish in the warp.
 #pragma once
 #include "arks_device.cuh"
+#include <cstdio>
 
 namespace arks {
 
@@ -22,8 +27,18 @@ constexpr int kMapThreads = kMapWarps * 32;
 constexpr int kRegionBases = 512;               // bases packed per region (32 lanes x 16)
 constexpr int kRegionWords = kRegionBases / 16 + 6;
 constexpr int kRegionInvWords = kRegionBases / 32 + 3;
-constexpr int kProbeBatch = 4;                  // windows per lane in flight
-constexpr int kMapMinBlocks = 2;                // CTAs per SM the register budget is sized for
+#ifndef ARKS_PROBE_BATCH
+#define ARKS_PROBE_BATCH 2
+#endif
+#ifndef ARKS_MAP_MIN_BLOCKS
+#define ARKS_MAP_MIN_BLOCKS 4
+#endif
+#ifndef ARKS_SEEDS
+#define ARKS_SEEDS 4
+#endif
+constexpr int kProbeBatch = ARKS_PROBE_BATCH;                  // windows per lane in flight
+constexpr int kSeeds = ARKS_SEEDS;                       // seed windows probed per mate
+constexpr int kMapMinBlocks = ARKS_MAP_MIN_BLOCKS;                // CTAs per SM the register budget is sized for
 
 struct MapCounters
 {
@@ -57,7 +72,30 @@ struct MapParams
 	uint64_t imap_mask;
 	unsigned long long* imap_count;
 	MapCounters* ctr;
+	// packed contig text for seed-and-extend (see ContigText in arks_index.cuh)
+	const uint32_t* ct_T;
+	const uint32_t* ct_TINS;
+	const uint32_t* ct_TUNIQ;
+	const uint64_t* ct_end_g0;
+	const uint32_t* ct_end_len;
+	const uint32_t* ct_end_cr;
+	uint64_t ct_n_bases;
+	int use_extension;
+	// exact integer forms of the two double-precision tests, built on the host with the
+	// reference's expressions (both tables have kRegionBases + 1 entries):
+	//   jmin[total] = smallest count with (double)count / (double)total > j_index (UINT32_MAX: none)
+	//   nmax[len]   = largest number of Ns with !((double)n / (double)len > 0.02)
+	const uint32_t* jmin;
+	const uint32_t* nmax;
+	// pairs the group kernel could not finish: indices + per-mate state (see kMate*)
+	uint32_t* worklist;
+	uint32_t* work_count;
+	uint32_t* mate_state; // 2 per pair
 };
+
+// mate_state values: a contig end (or 0) decided by the group kernel, or one of
+constexpr uint32_t kMateSlow = 0xFFFFFFFFu;    // valid pair, this mate still has to be resolved
+constexpr uint32_t kMateUnknown = 0xFFFFFFFEu; // nothing has been done for this pair yet
 
 struct LaneStats
 {
@@ -131,6 +169,42 @@ warp_pack(WarpRegion& R, const char* src, uint32_t len, uint32_t lane, uint32_t&
 	__syncwarp();
 }
 
+// Packs both mates in one pass (each <= 256 bases): lanes 0-15 pack mate 0, lanes 16-31
+// mate 1.  Returns, on every lane, the N / other-invalid counts of both mates.
+__device__ __forceinline__ void
+warp_pack2(WarpRegion* R, const char* s0, uint32_t l0, const char* s1, uint32_t l1, uint32_t lane, uint32_t& nn0, uint32_t& no0,
+    uint32_t& nn1, uint32_t& no1)
+{
+	const uint32_t half = lane >> 4, j = lane & 15u;
+	const uint32_t len = half ? l1 : l0;
+	const char* src = half ? s1 : s0;
+	const uint32_t nwords = (len + 15) >> 4;
+	uint32_t w = 0, inv16 = 0, nn = 0, no = 0;
+	if (j < nwords)
+		w = pack_group(src, len, j, &inv16, &nn, &no);
+	WarpRegion& Rr = R[half];
+	Rr.W[j] = w;
+	const uint32_t mirrored = __shfl_sync(0xFFFFFFFFu, w, (half << 4) | ((nwords - 1 - j) & 15u));
+	if (j < nwords)
+		Rr.RC[j] = rev2(~mirrored);
+	const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, inv16, 1);
+	if ((j & 1) == 0)
+		Rr.INV[j >> 1] = inv16 | (up << 16);
+	const uint32_t any = __ballot_sync(0xFFFFFFFFu, inv16 != 0);
+	nn0 = no0 = nn1 = no1 = 0;
+	if (any) {
+		// pack (n, other) of each half into one word per lane and add across the warp
+		const uint32_t v = nn | (no << 16);
+		const uint32_t lo = __reduce_add_sync(0xFFFFFFFFu, half ? 0u : v);
+		const uint32_t hi = __reduce_add_sync(0xFFFFFFFFu, half ? v : 0u);
+		nn0 = lo & 0xFFFFu;
+		no0 = lo >> 16;
+		nn1 = hi & 0xFFFFu;
+		no1 = hi >> 16;
+	}
+	__syncwarp();
+}
+
 // checkReadSequence's character classes for a read of any length, without packing
 __device__ __forceinline__ void
 warp_classify(const char* src, uint32_t len, uint32_t lane, uint32_t& n_n, uint32_t& n_other)
@@ -148,10 +222,14 @@ warp_classify(const char* src, uint32_t len, uint32_t lane, uint32_t& n_n, uint3
 }
 
 // checkReadSequence (Arcs.cpp:366-389): only ACGTN (any case), N fraction <= 0.02
-__device__ __forceinline__ bool read_ok(uint32_t n_n, uint32_t n_other, uint32_t len)
+__device__ __forceinline__ bool read_ok(uint32_t n_n, uint32_t n_other, uint32_t len, const uint32_t* nmax)
 {
 	if (n_other)
 		return false;
+	if (n_n == 0)
+		return true; // 0/len = 0 (or NaN for len 0): never > 0.02
+	if (len <= (uint32_t)kRegionBases)
+		return n_n <= nmax[len];
 	double ar = (double)n_n / (double)len;
 	return !(ar > 0.02);
 }
@@ -173,31 +251,36 @@ __device__ __forceinline__ void track_add(Track& t, uint32_t lane, uint32_t c, u
 	}
 }
 
-// bestContig's window loop (Arcs.cpp:957-994) over windows [0, nw) of a packed region of
-// Lc bases.
+// ---------------------------------------------------------------------------------------
+// Probing a list of windows of one packed region (bestContig's loop body, Arcs.cpp:957-994,
+// for the windows that could not be resolved by extension).  `list` == nullptr means the
+// windows are 0..n-1 themselves.  Does NOT count kv/ki (the caller classified the windows).
+// ---------------------------------------------------------------------------------------
+#ifdef ARKS_PROBE_INLINE
+#define ARKS_PROBE_ATTR __forceinline__
+#else
+#define ARKS_PROBE_ATTR __noinline__
+#endif
 template <int KW>
-__device__ __forceinline__ void
-warp_windows(const WarpRegion& R, uint32_t Lc, uint32_t nw, const MapParams& P, uint32_t lane, Track& tr, LaneStats& st)
+__device__ ARKS_PROBE_ATTR void
+warp_probe_windows(const WarpRegion& R, uint32_t Lc, const uint16_t* list, uint32_t n, const MapParams& P, uint32_t lane,
+    Track& tr, LaneStats& st)
 {
 	const uint32_t Lp = ((Lc + 15) >> 4) << 4;
 #pragma unroll 1
-	for (uint32_t base = 0; base < nw; base += 32 * kProbeBatch) {
+	for (uint32_t base = 0; base < n; base += 32 * kProbeBatch) {
 		Key128 key[kProbeBatch];
-		uint64_t hi[kProbeBatch], lo[kProbeBatch];
+		uint64_t hi[kProbeBatch], lo[kProbeBatch], pi;
 		uint32_t val[kProbeBatch];
 		uint32_t act = 0;
 #pragma unroll
 		for (int r = 0; r < kProbeBatch; ++r) {
-			uint32_t p = base + r * 32 + lane;
-			if (p < nw) {
-				if (window_invalid(R.INV, p, P.k)) {
-					st.ki++;
-				} else {
-					st.kv++;
-					act |= 1u << r;
-					key[r] = canonical_key<KW>(R.W, R.RC, p, P.k, Lp, P.mask_hi, P.mask_lo);
-					load_slot<KW>(P.table, hash_to_slot(key_hash<KW>(key[r]), P.nslots), hi[r], lo[r], val[r]);
-				}
+			uint32_t i = base + r * 32 + lane;
+			if (i < n) {
+				uint32_t p = list ? list[i] : i;
+				act |= 1u << r;
+				key[r] = canonical_key<KW>(R.W, R.RC, p, P.k, Lp, P.mask_hi, P.mask_lo);
+				load_slot(P.table, hash_to_slot(key_hash<KW>(key[r]), P.nslots), hi[r], lo[r], val[r], pi);
 			}
 		}
 		uint32_t hit[kProbeBatch];
@@ -205,16 +288,16 @@ warp_windows(const WarpRegion& R, uint32_t Lc, uint32_t nw, const MapParams& P, 
 		for (int r = 0; r < kProbeBatch; ++r) {
 			hit[r] = 0;
 			if (act & (1u << r)) {
-				bool found = hi[r] == key[r].hi && lo[r] == key[r].lo;
-				bool empty = hi[r] == kEmptyKey && (KW == 1 || lo[r] == kEmptyKey);
+				bool found = slot_matches<KW>(hi[r], lo[r], key[r]);
+				bool empty = slot_empty<KW>(hi[r], lo[r]);
 				if (!found && !empty) {
 					// rare: the home slot holds another key -- walk the probe sequence
 					uint64_t slot = hash_to_slot(key_hash<KW>(key[r]), P.nslots);
 					do {
 						slot = slot + 1 == P.nslots ? 0 : slot + 1;
-						load_slot<KW>(P.table, slot, hi[r], lo[r], val[r]);
-						found = hi[r] == key[r].hi && lo[r] == key[r].lo;
-						empty = hi[r] == kEmptyKey && (KW == 1 || lo[r] == kEmptyKey);
+						load_slot(P.table, slot, hi[r], lo[r], val[r], pi);
+						found = slot_matches<KW>(hi[r], lo[r], key[r]);
+						empty = slot_empty<KW>(hi[r], lo[r]);
 					} while (!found && !empty);
 				}
 				if (found) {
@@ -250,96 +333,355 @@ warp_windows(const WarpRegion& R, uint32_t Lc, uint32_t nw, const MapParams& P, 
 	}
 }
 
+// classify windows [0, nw) of a region as valid / invalid (kv / ki) without resolving them
+__device__ __forceinline__ void
+warp_count_windows(const WarpRegion& R, uint32_t nw, uint32_t k, uint32_t lane, uint16_t* list, uint32_t& n_list, LaneStats& st)
+{
+	n_list = 0;
+	for (uint32_t pb = 0; pb < nw; pb += 32) {
+		const uint32_t p = pb + lane;
+		bool need = false;
+		if (p < nw) {
+			if (window_invalid(R.INV, p, k)) {
+				st.ki++;
+			} else {
+				st.kv++;
+				need = true;
+			}
+		}
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+		if (need)
+			list[n_list + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+		n_list += __popc(m);
+	}
+	__syncwarp();
+}
+
 // bestContig's window loop for a read longer than one region: repack chunk by chunk (cold path)
 template <int KW>
 __device__ __noinline__ void
-warp_windows_long(WarpRegion& R, const char* src, uint32_t total, const MapParams& P, uint32_t lane, Track& tr, LaneStats& st)
+warp_windows_long(WarpRegion& R, uint16_t* list, const char* src, uint32_t total, const MapParams& P, uint32_t lane, Track& tr, LaneStats& st)
 {
 	const uint32_t cw = kRegionBases - P.k + 1;
 	for (uint32_t c0 = 0; c0 < total; c0 += cw) {
 		uint32_t nwc = min(cw, total - c0);
 		uint32_t Lc = nwc + P.k - 1;
-		uint32_t a, b;
+		uint32_t a, b, n_list;
 		__syncwarp();
 		warp_pack(R, src + c0, Lc, lane, a, b);
-		warp_windows<KW>(R, Lc, nwc, P, lane, tr, st);
+		warp_count_windows(R, nwc, P.k, lane, list, n_list, st);
+		warp_probe_windows<KW>(R, Lc, list, n_list, P, lane, tr, st);
 	}
 }
 
-template <int KW>
-__global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(MapParams P)
+// 16 mismatch bits (LSB-first by base) between a packed stream word and the contig text at
+// global base coordinate gb (may be out of range: then every base mismatches)
+__device__ __forceinline__ uint32_t mismatch16(uint32_t sword, const uint32_t* T, int64_t gb, int64_t n_bases)
 {
-	__shared__ WarpRegion regions[kMapWarps][2];
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t warp = threadIdx.x >> 5;
-	WarpRegion* R = regions[warp];
-	LaneStats st{0, 0, 0, 0, 0};
-	uint32_t pass = 0, fail = 0, stored = 0, invalid = 0, nogood = 0;
-	bool overflow = false;
-	const uint32_t nwarps = gridDim.x * kMapWarps;
-#pragma unroll 1
-	for (uint32_t pair = blockIdx.x * kMapWarps + warp; pair < P.n_pairs; pair += nwarps) {
-		const uint32_t o0 = P.read_off[2 * pair], o1 = P.read_off[2 * pair + 1], o2 = P.read_off[2 * pair + 2];
-		const uint32_t l1 = o1 - o0, l2 = o2 - o1;
-		const bool shortpair = l1 <= (uint32_t)kRegionBases && l2 <= (uint32_t)kRegionBases;
-		uint32_t nn1, no1, nn2, no2;
+	if (gb < 0 || gb + 16 > n_bases)
+		return 0xFFFFu;
+	const uint64_t wi = (uint64_t)gb >> 4;
+	const uint32_t sh = ((uint32_t)gb & 15u) * 2u;
+	const uint32_t t0 = __ldg(T + wi), t1 = __ldg(T + wi + 1);
+	const uint32_t t = __funnelshift_l(t1, t0, sh);
+	const uint32_t x = sword ^ t;
+	uint32_t mm = (x | (x >> 1)) & 0x55555555u; // bit (30-2i) = base i differs
+	uint32_t y = __brev(mm) >> 1;               // bit 2i = base i differs
+	y = (y | (y >> 1)) & 0x33333333u;
+	y = (y | (y >> 2)) & 0x0F0F0F0Fu;
+	y = (y | (y >> 4)) & 0x00FF00FFu;
+	y = (y | (y >> 8)) & 0x0000FFFFu;
+	return y;
+}
+
+struct Extension
+{
+	bool have;     // a seed hit established a diagonal
+	bool same;     // read and contig on the same strand
+	int64_t D;     // contig coordinate of stream coordinate 0
+	int64_t lo, hi; // the seed's contig end covers [lo, hi)
+	uint32_t c_end; // its contig-end record
+	uint32_t off;  // stream offset of read coordinate 0 in the RC stream (Lp - L)
+};
+
+// bestContig (Arcs.cpp:939-1014) for one prepacked mate.  Seed-and-extend: the seed's slot
+// says where its k-mer sits in the packed contig text; the read is compared with the text
+// along that diagonal, and every window whose k bases all match a window that mapKmers
+// inserted is resolved without touching the table (same key => same value; the value is the
+// contig end if the TUNIQ bit is set, else 0).  Everything else is probed as before.
+// `clean` = the mate has no invalid character at all (then no window is invalid).
+template <int KW>
+__device__ __forceinline__ void
+warp_resolve_read(const WarpRegion& R, uint32_t* M, uint16_t* list, uint32_t L, uint32_t total, bool clean, const Extension& E,
+    const MapParams& P, uint32_t lane, Track& tr, LaneStats& st)
+{
+	const uint32_t nwords = (L + 15) >> 4;
+	uint32_t n_list = 0;
+	if (E.have) {
+		// mismatch mask in stream coordinates; bases outside the read are forced to "match"
+		const uint32_t* S = E.same ? R.W : R.RC;
+		const uint32_t q0 = E.same ? 0u : E.off; // stream coordinate of the first read base / window
+		uint32_t m16 = 0;
+		if (lane < nwords) {
+			m16 = mismatch16(S[lane], P.ct_T, E.D + 16 * (int64_t)lane, (int64_t)P.ct_n_bases);
+			const uint32_t b0 = 16 * lane; // keep only stream coordinates in [q0, q0 + L)
+			const uint32_t lo = q0 > b0 ? min(q0 - b0, 16u) : 0u;
+			const uint32_t hi = q0 + L > b0 ? min(q0 + L - b0, 16u) : 0u;
+			m16 &= (hi > lo) ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+		}
+		const uint32_t any_mm = __ballot_sync(0xFFFFFFFFu, m16 != 0);
+		const int64_t gw0 = E.D + q0; // contig coordinate of stream window q0
+		const bool inside = gw0 >= E.lo && gw0 + (int64_t)(total - 1) + (int64_t)P.k <= E.hi;
+		if (any_mm == 0 && inside && clean) {
+			// ---- fast path: the whole mate equals the contig text: a window is found iff it was
+			// inserted, recorded iff its key is unique; word-parallel over the two bit masks
+			const uint64_t w0 = (uint64_t)gw0 >> 5;
+			const uint32_t sh = (uint32_t)gw0 & 31u;
+			const uint32_t nw_words = (sh + total + 31) >> 5; // <= 17
+			uint32_t ins = 0, uq = 0, range = 0;
+			if (lane < nw_words) {
+				const uint32_t first = lane == 0 ? sh : 0u;
+				const uint32_t last = min(32u, sh + total - 32u * lane); // exclusive
+				range = (last >= 32 ? 0xFFFFFFFFu : ((1u << last) - 1u)) & ~((1u << first) - 1u);
+				ins = __ldg(P.ct_TINS + w0 + lane) & range;
+				uq = __ldg(P.ct_TUNIQ + w0 + lane) & ins;
+			}
+			st.kv += lane == 0 ? total : 0u;
+			st.found += __popc(ins);
+			st.rec += __popc(uq);
+			st.dups += __popc(ins & ~uq);
+			const uint32_t cnt = warp_sum(__popc(uq));
+			if (cnt)
+				track_add(tr, lane, E.c_end, cnt);
+			// windows that were not inserted (skipped by the N walk): rare, probe them
+			uint32_t miss = range & ~ins;
+			const uint32_t any_miss = __ballot_sync(0xFFFFFFFFu, miss != 0);
+			if (any_miss) {
+				for (uint32_t src = 0; src < nw_words; ++src) {
+					uint32_t mw = __shfl_sync(0xFFFFFFFFu, miss, src);
+					if (lane == 0) {
+						while (mw) {
+							const uint32_t bit = __ffs(mw) - 1;
+							mw &= mw - 1;
+							const uint32_t q = (uint32_t)(((w0 + src) << 5) + bit - (uint64_t)E.D);
+							list[n_list++] = (uint16_t)(E.same ? q : (L - P.k) - (q - E.off));
+						}
+					}
+					n_list = __shfl_sync(0xFFFFFFFFu, n_list, 0);
+				}
+				__syncwarp();
+				warp_probe_windows<KW>(R, L, list, n_list, P, lane, tr, st);
+			}
+			return;
+		}
+		const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, m16, 1);
+		if ((lane & 1) == 0)
+			M[lane >> 1] = m16 | (up << 16);
 		__syncwarp();
-		if (shortpair) {
-			warp_pack(R[0], P.bases + o0, l1, lane, nn1, no1);
-			warp_pack(R[1], P.bases + o1, l2, lane, nn2, no2);
-		} else {
-			warp_classify(P.bases + o0, l1, lane, nn1, no1);
-			warp_classify(P.bases + o1, l2, lane, nn2, no2);
-		}
-		uint32_t c[2] = {0, 0};
-		if (read_ok(nn1, no1, l1) && read_ok(nn2, no2, l2)) {
-#pragma unroll 1
-			for (int rd = 0; rd < 2; ++rd) {
-				// bestContig (Arcs.cpp:939-1014) for mate rd
-				const uint32_t len = rd ? l2 : l1;
-				const uint32_t total = len >= P.k ? len - P.k + 1 : 0;
-				Track tr{0, 0, 0, false};
-				if (total) {
-					if (shortpair)
-						warp_windows<KW>(R[rd], len, total, P, lane, tr, st);
-					else
-						warp_windows_long<KW>(R[0], P.bases + (rd ? o1 : o0), total, P, lane, tr, st);
-				}
-				// argmax count, ties -> smallest contig end
-				uint32_t mycnt = lane < tr.n ? tr.cnt : 0;
-				uint32_t best_cnt = __reduce_max_sync(0xFFFFFFFFu, mycnt);
-				uint32_t cand = (best_cnt && lane < tr.n && tr.cnt == best_cnt) ? tr.c : 0xFFFFFFFFu;
-				uint32_t best_c = __reduce_min_sync(0xFFFFFFFFu, cand);
-				double maxj = best_cnt ? (double)best_cnt / (double)total : 0.0;
-				overflow |= tr.overflow;
-				if (maxj > P.j_index) {
-					pass++;
-					c[rd] = best_cnt ? best_c : 0;
-				} else {
-					fail++;
-				}
-			}
-		} else {
-			invalid++;
-		}
-		uint32_t out = 0;
-		if (c[0] != 0 && c[0] == c[1]) {
-			stored++;
-			out = c[0];
-			if (lane == 0) {
-				uint32_t cc = (P.remap && out < P.n_remap) ? P.remap[out] : out;
-				imap_add(P.imap, P.imap_mask, P.imap_count, P.barcode_id[pair], (cc - 1) >> 1, (cc & 1u), (cc & 1u) ^ 1u);
-			}
-		} else {
-			nogood++;
-		}
-		if (P.conreci_out && lane == 0)
-			P.conreci_out[pair] = (int32_t)out;
 	}
-	// flush counters: lane-private k-mer counters are summed over the warp, the per-pair /
-	// per-read counters are warp-uniform
-	uint32_t kv = warp_sum(st.kv), ki = warp_sum(st.ki), fo = warp_sum(st.found), re = warp_sum(st.rec),
-	         du = warp_sum(st.dups);
+	uint32_t ext_uniq = 0;
+	for (uint32_t pb = 0; pb < total; pb += 32) {
+		const uint32_t p = pb + lane;
+		bool need = false;
+		if (p < total) {
+			if (!clean && window_invalid(R.INV, p, P.k)) {
+				st.ki++;
+			} else {
+				st.kv++;
+				need = true;
+				if (E.have) {
+					const uint32_t q = E.same ? p : (L - P.k - p) + E.off;
+					if (!window_invalid(M, q, P.k)) {
+						const int64_t gw = E.D + q;
+						if (gw >= E.lo && gw + (int64_t)P.k <= E.hi) {
+							const uint32_t ins = __ldg(P.ct_TINS + (gw >> 5)) >> (gw & 31);
+							if (ins & 1u) {
+								need = false;
+								st.found++;
+								if ((__ldg(P.ct_TUNIQ + (gw >> 5)) >> (gw & 31)) & 1u) {
+									st.rec++;
+									ext_uniq++;
+								} else {
+									st.dups++;
+								}
+							}
+						}
+					}
+				}
+			}
+		}
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+		if (need)
+			list[n_list + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+		n_list += __popc(m);
+	}
+	__syncwarp();
+	if (E.have) {
+		const uint32_t cnt = warp_sum(ext_uniq);
+		if (cnt)
+			track_add(tr, lane, E.c_end, cnt);
+	}
+	warp_probe_windows<KW>(R, L, list, n_list, P, lane, tr, st);
+}
+
+// warp-uniform per-pair / per-read counters
+struct PairCounters
+{
+	uint32_t pass, fail, stored, invalid, nogood;
+	bool overflow;
+};
+
+// argmax over the vote table (ties -> smallest contig end) + Jaccard gate (Arcs.cpp:996-1012).
+// Returns the read's contig end or 0; *passed tells which Jaccard counter to bump.
+__device__ __forceinline__ uint32_t
+warp_decide(const Track& tr, uint32_t total, const MapParams& P, uint32_t lane, bool* passed)
+{
+	const uint32_t mycnt = lane < tr.n ? tr.cnt : 0;
+	const uint32_t best_cnt = __reduce_max_sync(0xFFFFFFFFu, mycnt);
+	const uint32_t cand = (best_cnt && lane < tr.n && tr.cnt == best_cnt) ? tr.c : 0xFFFFFFFFu;
+	const uint32_t best_c = __reduce_min_sync(0xFFFFFFFFu, cand);
+	bool ok;
+	if (best_cnt == 0)
+		ok = 0.0 > P.j_index;
+	else if (total <= (uint32_t)kRegionBases)
+		ok = best_cnt >= __ldg(P.jmin + total);
+	else
+		ok = (double)best_cnt / (double)total > P.j_index;
+	*passed = ok;
+	return (ok && best_cnt) ? best_c : 0u;
+}
+
+// One read pair handled by the whole warp (any read length).  Generic path.
+// state0/state1: kMateUnknown for a pair nobody has looked at (validity is checked here), else
+// per mate either kMateSlow (resolve it here) or the contig end already decided elsewhere
+// (then that mate is not touched and none of its counters are bumped).
+template <int KW>
+__device__ __noinline__ uint32_t
+warp_process_pair(uint32_t pair, uint32_t state0, uint32_t state1, const MapParams& P, WarpRegion* R, uint32_t* M, uint16_t* list,
+    uint32_t lane, LaneStats& st, PairCounters& pc)
+{
+	const bool fresh = state0 == kMateUnknown;
+	const bool todo0 = fresh || state0 == kMateSlow, todo1 = fresh || state1 == kMateSlow;
+	const uint32_t o0 = P.read_off[2 * pair], o1 = P.read_off[2 * pair + 1], o2 = P.read_off[2 * pair + 2];
+	const uint32_t l1 = o1 - o0, l2 = o2 - o1;
+	const bool shortpair = l1 <= (uint32_t)kRegionBases && l2 <= (uint32_t)kRegionBases;
+	uint32_t nn1, no1, nn2, no2;
+	__syncwarp();
+	if (l1 <= 256u && l2 <= 256u) {
+		warp_pack2(R, P.bases + o0, l1, P.bases + o1, l2, lane, nn1, no1, nn2, no2);
+	} else if (shortpair) {
+		warp_pack(R[0], P.bases + o0, l1, lane, nn1, no1);
+		warp_pack(R[1], P.bases + o1, l2, lane, nn2, no2);
+	} else {
+		warp_classify(P.bases + o0, l1, lane, nn1, no1);
+		warp_classify(P.bases + o1, l2, lane, nn2, no2);
+	}
+	uint32_t c[2] = {fresh ? 0u : state0, fresh ? 0u : state1};
+	if (!fresh || (read_ok(nn1, no1, l1, P.nmax) && read_ok(nn2, no2, l2, P.nmax))) {
+		// ---- seeds of both mates in one round: lanes [0,kSeeds) mate 0, [kSeeds,2kSeeds) mate 1
+		uint64_t seed_pos = 0;
+		uint32_t seed_p = 0;
+		bool seed_found = false, seed_fc = false;
+		if (shortpair && P.use_extension) {
+			const uint32_t rd = lane / kSeeds, sidx = lane % kSeeds;
+			const uint32_t len = rd ? l2 : l1;
+			if (lane < 2 * kSeeds && len >= P.k && (rd ? todo1 : todo0)) {
+				const uint32_t total = len - P.k + 1;
+				seed_p = kSeeds > 1 ? (uint32_t)(((uint64_t)(total - 1) * sidx) / (kSeeds - 1)) : 0;
+				const WarpRegion& Rr = R[rd];
+				if (!window_invalid(Rr.INV, seed_p, P.k)) {
+					const uint32_t Lp = ((len + 15) >> 4) << 4;
+					Key128 key = canonical_key<KW>(Rr.W, Rr.RC, seed_p, P.k, Lp, P.mask_hi, P.mask_lo, &seed_fc);
+					uint64_t slot = hash_to_slot(key_hash<KW>(key), P.nslots);
+					while (true) {
+						uint64_t hi, lo;
+						uint32_t val;
+						load_slot(P.table, slot, hi, lo, val, seed_pos);
+						if (slot_matches<KW>(hi, lo, key)) {
+							seed_found = true;
+							break;
+						}
+						if (slot_empty<KW>(hi, lo))
+							break;
+						slot = slot + 1 == P.nslots ? 0 : slot + 1;
+					}
+				}
+			}
+		}
+		const uint32_t seed_votes = __ballot_sync(0xFFFFFFFFu, seed_found);
+#pragma unroll 1
+		for (int rd = 0; rd < 2; ++rd) {
+			// bestContig (Arcs.cpp:939-1014) for mate rd
+			if (!(rd ? todo1 : todo0))
+				continue;
+			const uint32_t len = rd ? l2 : l1;
+			const uint32_t total = len >= P.k ? len - P.k + 1 : 0;
+			Track tr{0, 0, 0, false};
+			if (total) {
+				if (shortpair) {
+					Extension E{};
+					const uint32_t mine = (seed_votes >> (rd * kSeeds)) & ((1u << kSeeds) - 1u);
+					E.have = mine != 0;
+					if (E.have) {
+						const int src = rd * kSeeds + __ffs(mine) - 1;
+						const uint64_t pi = __shfl_sync(0xFFFFFFFFu, seed_pos, src);
+						const uint32_t sp = __shfl_sync(0xFFFFFFFFu, seed_p, src);
+						const bool r_fc = __shfl_sync(0xFFFFFFFFu, (int)seed_fc, src);
+						const bool c_fc = (pi >> kPosBits) & 1ull;
+						const uint64_t g = pi & kPosMask;
+						const uint32_t eidx = (uint32_t)(pi >> 40);
+						E.same = r_fc == c_fc;
+						E.off = (((len + 15) >> 4) << 4) - len;
+						E.D = E.same ? (int64_t)g - (int64_t)sp : (int64_t)g - (int64_t)((len - P.k - sp) + E.off);
+						E.lo = (int64_t)__ldg(P.ct_end_g0 + eidx);
+						E.hi = E.lo + (int64_t)__ldg(P.ct_end_len + eidx);
+						E.c_end = __ldg(P.ct_end_cr + eidx);
+					}
+					const bool clean = (rd ? (nn2 | no2) : (nn1 | no1)) == 0;
+					warp_resolve_read<KW>(R[rd], M, list, len, total, clean, E, P, lane, tr, st);
+				} else {
+					warp_windows_long<KW>(R[0], list, P.bases + (rd ? o1 : o0), total, P, lane, tr, st);
+				}
+			}
+			bool passed;
+			c[rd] = warp_decide(tr, total, P, lane, &passed);
+			pc.overflow |= tr.overflow;
+			if (passed)
+				pc.pass++;
+			else
+				pc.fail++;
+		}
+	} else {
+		pc.invalid++;
+	}
+	uint32_t out = 0;
+	if (c[0] != 0 && c[0] == c[1]) {
+		pc.stored++;
+		out = c[0];
+		if (lane == 0) {
+			uint32_t cc = (P.remap && out < P.n_remap) ? P.remap[out] : out;
+			imap_add(P.imap, P.imap_mask, P.imap_count, P.barcode_id[pair], (cc - 1) >> 1, (cc & 1u), (cc & 1u) ^ 1u);
+		}
+	} else {
+		pc.nogood++;
+	}
+	if (P.conreci_out && lane == 0)
+		P.conreci_out[pair] = (int32_t)out;
+	return out;
+}
+
+__device__ __forceinline__ void
+flush_counters(const MapParams& P, uint32_t lane, const LaneStats& st, uint32_t pass, uint32_t fail, uint32_t stored, uint32_t invalid,
+    uint32_t nogood, bool overflow)
+{
+	// every counter is a lane-private partial sum
+	const uint32_t kv = warp_sum(st.kv), ki = warp_sum(st.ki), fo = warp_sum(st.found), re = warp_sum(st.rec), du = warp_sum(st.dups);
+	pass = warp_sum(pass);
+	fail = warp_sum(fail);
+	stored = warp_sum(stored);
+	invalid = warp_sum(invalid);
+	nogood = warp_sum(nogood);
+	const uint32_t ov = __ballot_sync(0xFFFFFFFFu, overflow);
 	if (lane == 0) {
 		MapCounters* ctr = P.ctr;
 		if (kv) atomicAdd(&ctr->kmers_valid, (unsigned long long)kv);
@@ -352,8 +694,312 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(M
 		if (stored) atomicAdd(&ctr->pairs_stored, (unsigned long long)stored);
 		if (invalid) atomicAdd(&ctr->pairs_invalid, (unsigned long long)invalid);
 		if (nogood) atomicAdd(&ctr->pairs_nogood, (unsigned long long)nogood);
-		if (overflow) atomicAdd(&ctr->overflow, 1ull);
+		if (ov) atomicAdd(&ctr->overflow, 1ull);
 	}
+}
+
+// ---- warp-per-pair kernel (generic; kept for A/B runs: ARKS_MAP_MODE=pair) ------------------
+template <int KW>
+__global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(MapParams P)
+{
+	__shared__ WarpRegion regions[kMapWarps][2];
+	__shared__ uint32_t Ms[kMapWarps][kRegionInvWords];
+	__shared__ uint16_t lists[kMapWarps][kRegionBases];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5;
+	LaneStats st{0, 0, 0, 0, 0};
+	PairCounters pc{0, 0, 0, 0, 0, false};
+	const uint32_t nwarps = gridDim.x * kMapWarps;
+#pragma unroll 1
+	for (uint32_t pair = blockIdx.x * kMapWarps + warp; pair < P.n_pairs; pair += nwarps)
+		warp_process_pair<KW>(pair, kMateUnknown, kMateUnknown, P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
+	const bool l0 = lane == 0; // pair counters are warp-uniform: count them once
+	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,
+	    pc.overflow);
+}
+
+// ---- warp-per-16-pairs kernel -----------------------------------------------------------------
+// A warp takes a group of 16 consecutive pairs = 32 reads.
+//   stage 1  all lanes pack the 32 reads to 2 bits (flat over the reads' 16-base words, so no lane
+//            idles), invalid-base masks alongside;
+//   stage 2  ONE LANE PER READ: seed probes (two in flight per lane, 64 per warp), the
+//            comparison with the packed contig text along the seed's diagonal, and the
+//            word-parallel inserted/unique mask test.  A read that equals the contig text -- the
+//            common case -- is finished here, with no lane idle;
+//   stage 3  one lane per pair: if both mates are finished, the pair rule (Arcs.cpp:1280) and
+//            the barcode tally; otherwise the pair goes to a work list with the state of each
+//            mate, and map_slow_kernel resolves the unfinished mates (mismatches, Ns, no seed
+//            hit, not fully inside a contig end, reads longer than kGroupReadBases) with the
+//            general warp-per-pair path.
+#ifndef ARKS_GROUP_WARPS
+#define ARKS_GROUP_WARPS 8
+#endif
+#ifndef ARKS_GROUP_MIN_BLOCKS
+#define ARKS_GROUP_MIN_BLOCKS 4
+#endif
+constexpr int kGroupWarps = ARKS_GROUP_WARPS;
+constexpr int kGroupThreads = kGroupWarps * 32;
+constexpr int kGroupMinBlocks = ARKS_GROUP_MIN_BLOCKS;
+constexpr int kGroupPairs = 16;
+constexpr int kGroupReadBases = 256;
+constexpr int kGroupWStride = kGroupReadBases / 16 + 5; // 21 words: odd stride, +4 slack for extraction
+constexpr int kGroupIStride = kGroupReadBases / 32 + 3; // 11 words
+
+struct GroupSmem
+{
+	uint32_t W[32][kGroupWStride];
+	uint32_t INV[32][kGroupIStride];
+	uint32_t woff[33];
+	uint32_t nbad[32]; // per read: N count | other-invalid count << 16
+};
+
+template <int KW>
+__global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_kernel(MapParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	GroupSmem& G = reinterpret_cast<GroupSmem*>(smem_raw)[threadIdx.x >> 5];
+	const uint32_t lane = threadIdx.x & 31;
+	LaneStats st{0, 0, 0, 0, 0};
+	uint32_t pass = 0, fail = 0, stored = 0, invalid = 0, nogood = 0;
+	bool overflow = false;
+	const uint32_t n_groups = (P.n_pairs + kGroupPairs - 1) / kGroupPairs;
+	const uint32_t nwarps = gridDim.x * kGroupWarps;
+#pragma unroll 1
+	for (uint32_t group = blockIdx.x * kGroupWarps + (threadIdx.x >> 5); group < n_groups; group += nwarps) {
+		const uint32_t pair0 = group * kGroupPairs;
+		const uint32_t my_pair = pair0 + (lane >> 1);
+		const bool exists = my_pair < P.n_pairs;
+		// ---- read lane's extent
+		uint32_t off = 0, len = 0;
+		if (exists) {
+			off = P.read_off[2 * pair0 + lane];
+			len = P.read_off[2 * pair0 + lane + 1] - off;
+		}
+		const bool is_long = len > (uint32_t)kGroupReadBases;
+		const uint32_t long_pairs = __ballot_sync(0xFFFFFFFFu, is_long);
+		const bool pair_long = ((long_pairs >> (lane & ~1u)) & 3u) != 0;
+		const uint32_t nwords = (exists && !pair_long) ? (len + 15) >> 4 : 0;
+		// ---- stage 1: flat packing
+		uint32_t incl = nwords;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= (uint32_t)o)
+				incl += t;
+		}
+		__syncwarp();
+		G.woff[lane + 1] = incl;
+		if (lane == 0)
+			G.woff[0] = 0;
+		G.nbad[lane] = 0;
+		const uint32_t total_words = __shfl_sync(0xFFFFFFFFu, incl, 31);
+		__syncwarp();
+		for (uint32_t f = lane; f < total_words; f += 32) {
+			// read r with woff[r] <= f < woff[r+1]
+			uint32_t r = 0;
+#pragma unroll
+			for (int step = 16; step > 0; step >>= 1)
+				if (G.woff[r + step] <= f)
+					r += step;
+			const uint32_t j = f - G.woff[r];
+			const uint32_t roff = P.read_off[2 * pair0 + r];
+			const uint32_t rlen = P.read_off[2 * pair0 + r + 1] - roff;
+			uint32_t inv16, nn, no;
+			G.W[r][j] = pack_group(P.bases + roff, rlen, j, &inv16, &nn, &no);
+			reinterpret_cast<uint16_t*>(G.INV[r])[j] = (uint16_t)inv16;
+			if (inv16)
+				atomicAdd(&G.nbad[r], nn | (no << 16));
+		}
+		__syncwarp();
+		// ---- stage 2: one lane per read
+		const uint32_t bad = G.nbad[lane];
+		const uint32_t n_n = bad & 0xFFFFu, n_other = bad >> 16;
+		const bool clean = bad == 0;
+		const bool ok = exists && !pair_long && read_ok(n_n, n_other, len, P.nmax);
+		const bool mate_ok = __shfl_xor_sync(0xFFFFFFFFu, (int)ok, 1); // (not inside '&&': every lane must shuffle)
+		const bool pair_ok = ok && mate_ok;
+		const uint32_t total = (len >= P.k) ? len - P.k + 1 : 0;
+		uint32_t c_read = 0;      // the read's contig end (bestContig's return value)
+		bool need_slow = false;   // read must go through the warp-wide path
+		bool have_seed = false;
+		uint64_t seed_pi = 0;
+		uint32_t seed_p = 0;
+		bool seed_fc = false;
+		if (pair_ok && total) {
+			need_slow = true;
+			if (P.use_extension) {
+				const uint32_t* Wr = G.W[lane];
+				// seeds, two probes in flight
+#pragma unroll 1
+				for (uint32_t s0 = 0; s0 < (uint32_t)kSeeds && !have_seed; s0 += 2) {
+					Key128 key[2];
+					uint64_t hi[2], lo[2], pi[2];
+					uint32_t val[2], sp[2];
+					bool fc[2], act[2];
+#pragma unroll
+					for (int u = 0; u < 2; ++u) {
+						const uint32_t sidx = s0 + u;
+						sp[u] = kSeeds > 1 ? (uint32_t)(((uint64_t)(total - 1) * sidx) / (kSeeds - 1)) : 0;
+						act[u] = sidx < (uint32_t)kSeeds && (clean || !window_invalid(G.INV[lane], sp[u], P.k));
+						if (act[u]) {
+							Key128 f = extract_window<KW>(Wr, sp[u], P.mask_hi, P.mask_lo);
+							key[u] = canonical_from_forward<KW>(f, P.k, &fc[u]);
+							load_slot(P.table, hash_to_slot(key_hash<KW>(key[u]), P.nslots), hi[u], lo[u], val[u], pi[u]);
+						}
+					}
+#pragma unroll
+					for (int u = 0; u < 2; ++u) {
+						if (act[u] && !have_seed) {
+							bool found = slot_matches<KW>(hi[u], lo[u], key[u]);
+							bool empty = slot_empty<KW>(hi[u], lo[u]);
+							if (!found && !empty) {
+								uint64_t slot = hash_to_slot(key_hash<KW>(key[u]), P.nslots);
+								do {
+									slot = slot + 1 == P.nslots ? 0 : slot + 1;
+									load_slot(P.table, slot, hi[u], lo[u], val[u], pi[u]);
+									found = slot_matches<KW>(hi[u], lo[u], key[u]);
+									empty = slot_empty<KW>(hi[u], lo[u]);
+								} while (!found && !empty);
+							}
+							if (found) {
+								have_seed = true;
+								seed_pi = pi[u];
+								seed_p = sp[u];
+								seed_fc = fc[u];
+							}
+						}
+					}
+				}
+				if (have_seed && clean) {
+					// diagonal of the seed
+					const bool c_fc = (seed_pi >> kPosBits) & 1ull;
+					const uint64_t g = seed_pi & kPosMask;
+					const uint32_t eidx = (uint32_t)(seed_pi >> 40);
+					const bool same = seed_fc == c_fc;
+					const uint32_t nw = (len + 15) >> 4;
+					const uint32_t roff_s = (nw << 4) - len; // RC-stream coordinate of read base 0
+					const uint32_t q0 = same ? 0u : roff_s;
+					const int64_t D = same ? (int64_t)g - (int64_t)seed_p : (int64_t)g - (int64_t)((len - P.k - seed_p) + roff_s);
+					const int64_t e_lo = (int64_t)__ldg(P.ct_end_g0 + eidx);
+					const int64_t e_hi = e_lo + (int64_t)__ldg(P.ct_end_len + eidx);
+					const int64_t gw0 = D + q0;
+					if (gw0 >= e_lo && gw0 + (int64_t)(total - 1) + (int64_t)P.k <= e_hi) {
+						// the read against the contig text, 16 bases at a time
+						uint32_t mm = 0;
+#pragma unroll 1
+						for (uint32_t j = 0; j < nw && !mm; ++j) {
+							const uint32_t sw = same ? Wr[j] : rev2(~Wr[nw - 1 - j]);
+							uint32_t m16 = mismatch16(sw, P.ct_T, D + 16 * (int64_t)j, (int64_t)P.ct_n_bases);
+							const uint32_t b0 = 16 * j;
+							const uint32_t lo_b = q0 > b0 ? min(q0 - b0, 16u) : 0u;
+							const uint32_t hi_b = q0 + len > b0 ? min(q0 + len - b0, 16u) : 0u;
+							m16 &= (hi_b > lo_b) ? (((1u << hi_b) - 1u) & ~((1u << lo_b) - 1u)) : 0u;
+							mm |= m16;
+						}
+						if (!mm) {
+							// found iff inserted, recorded iff unique: word-parallel over the bit masks
+							const uint64_t w0 = (uint64_t)gw0 >> 5;
+							const uint32_t sh = (uint32_t)gw0 & 31u;
+							const uint32_t nww = (sh + total + 31) >> 5;
+							uint32_t n_ins = 0, n_uq = 0, n_miss = 0;
+#pragma unroll 1
+							for (uint32_t w = 0; w < nww; ++w) {
+								const uint32_t first = w == 0 ? sh : 0u;
+								const uint32_t last = min(32u, sh + total - 32u * w);
+								const uint32_t range = (last >= 32 ? 0xFFFFFFFFu : ((1u << last) - 1u)) & ~((1u << first) - 1u);
+								const uint32_t ins = __ldg(P.ct_TINS + w0 + w) & range;
+								const uint32_t uq = __ldg(P.ct_TUNIQ + w0 + w) & ins;
+								n_ins += __popc(ins);
+								n_uq += __popc(uq);
+								n_miss += __popc(range & ~ins);
+							}
+							if (n_miss == 0) {
+								need_slow = false;
+								st.kv += total;
+								st.found += n_ins;
+								st.rec += n_uq;
+								st.dups += n_ins - n_uq;
+								bool passed;
+								if (n_uq == 0)
+									passed = 0.0 > P.j_index;
+								else
+									passed = n_uq >= __ldg(P.jmin + total);
+								if (passed) {
+									pass++;
+									c_read = n_uq ? __ldg(P.ct_end_cr + eidx) : 0u;
+								} else {
+									fail++;
+								}
+							}
+						}
+					}
+				}
+			}
+		} else if (pair_ok) {
+			// shorter than k: bestContig returns 0 after an empty loop (maxjaccard 0)
+			if (0.0 > P.j_index)
+				pass++;
+			else
+				fail++;
+		}
+		// ---- stage 3: the pair rule for pairs whose mates are both finished (one lane per pair,
+		// Arcs.cpp:1280); every other valid pair goes to the work list of map_slow_kernel
+		const uint32_t c_mate = __shfl_xor_sync(0xFFFFFFFFu, c_read, 1);
+		const bool mate_slow = __shfl_xor_sync(0xFFFFFFFFu, (int)need_slow, 1);
+		const bool even = (lane & 1) == 0;
+		const bool defer = exists && even && (pair_long || (pair_ok && (need_slow || mate_slow)));
+		const uint32_t defer_mask = __ballot_sync(0xFFFFFFFFu, defer);
+		if (defer_mask) {
+			uint32_t base = 0;
+			if (lane == 0)
+				base = atomicAdd(P.work_count, (uint32_t)__popc(defer_mask));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (defer) {
+				P.worklist[base + __popc(defer_mask & ((1u << lane) - 1u))] = my_pair;
+				P.mate_state[2 * my_pair] = pair_long ? kMateUnknown : (need_slow ? kMateSlow : c_read);
+				P.mate_state[2 * my_pair + 1] = pair_long ? kMateUnknown : (mate_slow ? kMateSlow : c_mate);
+			}
+		}
+		if (exists && even && !defer) {
+			uint32_t out = 0;
+			if (!pair_ok)
+				invalid++;
+			if (c_read != 0 && c_read == c_mate) {
+				stored++;
+				out = c_read;
+				const uint32_t cc = (P.remap && out < P.n_remap) ? P.remap[out] : out;
+				imap_add(P.imap, P.imap_mask, P.imap_count, P.barcode_id[my_pair], (cc - 1) >> 1, (cc & 1u), (cc & 1u) ^ 1u);
+			} else {
+				nogood++;
+			}
+			if (P.conreci_out)
+				P.conreci_out[my_pair] = (int32_t)out;
+		}
+	}
+	(void)overflow;
+	flush_counters(P, lane, st, pass, fail, stored, invalid, nogood, overflow);
+}
+
+// ---- the pairs the group kernel deferred: one warp per pair, general path -------------------
+template <int KW>
+__global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_slow_kernel(MapParams P)
+{
+	__shared__ WarpRegion regions[kMapWarps][2];
+	__shared__ uint32_t Ms[kMapWarps][kRegionInvWords];
+	__shared__ uint16_t lists[kMapWarps][kRegionBases];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5;
+	LaneStats st{0, 0, 0, 0, 0};
+	PairCounters pc{0, 0, 0, 0, 0, false};
+	const uint32_t n_work = *P.work_count;
+	const uint32_t nwarps = gridDim.x * kMapWarps;
+#pragma unroll 1
+	for (uint32_t i = blockIdx.x * kMapWarps + warp; i < n_work; i += nwarps) {
+		const uint32_t pair = P.worklist[i];
+		warp_process_pair<KW>(pair, P.mate_state[2 * pair], P.mate_state[2 * pair + 1], P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
+	}
+	const bool l0 = lane == 0;
+	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,
+	    pc.overflow);
 }
 
 } // namespace arks

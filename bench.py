@@ -380,8 +380,9 @@ def main():
     ms_per_step = ms_max / args.steps
     value = float(k_all.item()) / (ms_per_step / 1000.0)
 
-    # roofline of the dominant kernel (map_pairs_kernel): algorithmic bytes / measured launch time (this rank)
-    launch_ms = ms / gpu_launches
+    # roofline of the lookup kernels: one batch = map_groups_kernel (lane-per-read fast path) + map_slow_kernel
+    # (the deferred mates); algorithmic bytes of the batch / measured duration of the pair of launches (this rank)
+    launch_ms = ms / (args.steps * n_batches)
     achieved = BYTES_PER_KMER * (kmers_per_step / n_batches) / (launch_ms / 1000.0) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -479,7 +480,7 @@ def main():
             },
             "clocks": clk, "gpu_launches": int(gpu_launches), "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "map_pairs_kernel<2>", "bytes_per_kmer": BYTES_PER_KMER,
+                         "traffic": traffic, "kernel": "map_groups_kernel<2> + map_slow_kernel<2> (one batch)", "bytes_per_kmer": BYTES_PER_KMER,
                          "peak_source": peak_src, "launch_ms": launch_ms},
             "cpu_baseline": cpu,
         }
