@@ -1,0 +1,1102 @@
+// arcs_main.cpp -- `arcs --arks` drop-in: same flags, defaults, input formats and output files as
+// bcgsc/arcs 1.2.8 (Arcs/Arcs.cpp main/runArcs, :1810-2184), with the ARKS hot path
+// (contig-end k-mer index, read-pair lookup + vote, barcode tally, pair links) running on the
+// GPU through the C ABI of libarks_b200.so.  Host side = parsing, barcode interning, graph +
+// writers.  No CPU fallback for the hot path.
+//
+// Differences from the reference, all outside the result files:
+//  * reads are parsed ONCE: barcode multiplicities are counted while mapping; because the
+//    reference's only use of the multiplicity before pairContigs is "is this barcode known"
+//    (Arcs.cpp:1257-1267), mapping first and filtering later gives the same imap.  If -m is
+//    given as an inverted range (min >= max), where the reference's `goodmult` test can fail,
+//    the reads are counted in a separate first pass exactly as the reference does.
+//  * -t is accepted and ignored (the GPU does the mapping); --gpus N (or ARKS_GPUS) shards
+//    read pairs by barcode across N GPUs.
+//  * -D (distance estimation) and the alignment (non --arks) mode are not implemented.
+#include "../../include/arks_b200.h"
+#include "seq_reader.h"
+
+#include <algorithm>
+#include <cassert>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <getopt.h>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <unistd.h>
+#include <unordered_map>
+#include <vector>
+
+#define PROGRAM "arcs"
+#define PACKAGE_VERSION "1.2.8-b200"
+
+using arks_host::SeqReader;
+using arks_host::SeqRecord;
+
+namespace {
+
+// ---- parameters: ARCS::ArcsParams (Arcs/Arcs.h:43-103), same defaults -----------------------
+struct Params
+{
+	std::string file, fofName, base_name, dist_graph_name, tsv_name, barcode_counts_name, multfile;
+	std::string dist_samples_tsv, dist_tsv;
+	int seq_id = 98, min_reads = 5, min_links = 0, min_size = 500, min_mult = 50, max_mult = 10000, max_degree = 0,
+	    end_length = 30000, verbose = 0, k_value = 30;
+	unsigned gap = 100, threads = 1, dist_bin_size = 20;
+	float error_percent = 0.05f;
+	double j_index = 0.55;
+	bool arks = false, dist_est = false, output_pair = false, dist_upper = false;
+	int gpus = 1;
+	bool two_pass = false;
+};
+Params params;
+
+const char USAGE[] =
+    "Usage: " PROGRAM " --arks -f CONTIGS.fa [OPTION]... READS.fq[.gz]...\n"
+    "B200-native ARKS (k-mer) mode of ARCS.  Options (as in arcs " PACKAGE_VERSION "):\n"
+    "   -f, --file=FILE       FASTA file of contig sequences to scaffold (required)\n"
+    "   -a, --fofName=FILE    text file listing input read files\n"
+    "   -u, --multfile=FILE   tsv or csv file listing barcode multiplicities\n"
+    "   -c, --min_reads=N     min aligned read pairs per barcode mapping [5]\n"
+    "   -k, --k_value=N       size of a k-mer [30] (4..64)\n"
+    "   -j, --j_index=N       min fraction of read kmers matching a contigId [0.55]\n"
+    "   -t, --threads=N       accepted for compatibility; the GPU does the mapping\n"
+    "   -l, --min_links=N     min shared barcodes between contigs [0]\n"
+    "   -z, --min_size=N      min contig length [500]\n"
+    "   -b, --base_name=STR   output file prefix\n"
+    "   -g, --graph=FILE      write the ABySS dist.gv to FILE\n"
+    "       --gap=N           fixed gap size for ABySS dist.gv file [100]\n"
+    "       --tsv=FILE        write graph in TSV format to FILE\n"
+    "       --barcode-counts=FILE       write number of reads per barcode to FILE\n"
+    "   -m, --index_multiplicity=RANGE  barcode multiplicity range [50-10000]\n"
+    "   -d, --max_degree=N    max node degree in scaffold graph [0]\n"
+    "   -e, --end_length=N    contig head/tail length for masking alignments [30000]\n"
+    "   -r, --error_percent=N p-value for head/tail assignment and link orientation [0.05]\n"
+    "   -P, --pair            output scaffolds pairing TSV\n"
+    "   -v, --run_verbose     verbose logging\n"
+    "       --gpus=N          number of GPUs to shard read pairs over [1]\n"
+    "       --arks            k-mer method (required)\n";
+
+enum
+{
+	OPT_HELP = 1000,
+	OPT_VERSION,
+	OPT_BX,
+	OPT_GAP,
+	OPT_TSV,
+	OPT_BARCODE_COUNTS,
+	OPT_SAMPLES_TSV,
+	OPT_DIST_TSV,
+	OPT_NO_DIST_EST,
+	OPT_DIST_MEDIAN,
+	OPT_DIST_UPPER,
+	OPT_ARKS_METHOD,
+	OPT_GPUS,
+	OPT_TWO_PASS
+};
+
+const char shortopts[] = "f:a:B:s:c:Dl:z:b:g:m:d:e:r:vt:u:j:k:P";
+const struct option longopts[] = { { "file", required_argument, NULL, 'f' },
+	                               { "fofName", required_argument, NULL, 'a' },
+	                               { "bin_size", required_argument, NULL, 'B' },
+	                               { "bx", no_argument, NULL, OPT_BX },
+	                               { "samples_tsv", required_argument, NULL, OPT_SAMPLES_TSV },
+	                               { "dist_tsv", required_argument, NULL, OPT_DIST_TSV },
+	                               { "seq_id", required_argument, NULL, 's' },
+	                               { "min_reads", required_argument, NULL, 'c' },
+	                               { "dist_est", no_argument, NULL, 'D' },
+	                               { "no_dist_est", no_argument, NULL, OPT_NO_DIST_EST },
+	                               { "dist_median", no_argument, NULL, OPT_DIST_MEDIAN },
+	                               { "dist_upper", no_argument, NULL, OPT_DIST_UPPER },
+	                               { "min_links", required_argument, NULL, 'l' },
+	                               { "min_size", required_argument, NULL, 'z' },
+	                               { "base_name", required_argument, NULL, 'b' },
+	                               { "graph", required_argument, NULL, 'g' },
+	                               { "tsv", required_argument, NULL, OPT_TSV },
+	                               { "barcode-counts", required_argument, NULL, OPT_BARCODE_COUNTS },
+	                               { "gap", required_argument, NULL, OPT_GAP },
+	                               { "index_multiplicity", required_argument, NULL, 'm' },
+	                               { "max_degree", required_argument, NULL, 'd' },
+	                               { "end_length", required_argument, NULL, 'e' },
+	                               { "error_percent", required_argument, NULL, 'r' },
+	                               { "run_verbose", required_argument, NULL, 'v' },
+	                               { "version", no_argument, NULL, OPT_VERSION },
+	                               { "help", no_argument, NULL, OPT_HELP },
+	                               { "threads", required_argument, NULL, 't' },
+	                               { "multfile", required_argument, NULL, 'u' },
+	                               { "k_value", required_argument, NULL, 'k' },
+	                               { "j_index", required_argument, NULL, 'j' },
+	                               { "arks", no_argument, NULL, OPT_ARKS_METHOD },
+	                               { "pair", no_argument, NULL, 'P' },
+	                               { "gpus", required_argument, NULL, OPT_GPUS },
+	                               { "two-pass", no_argument, NULL, OPT_TWO_PASS },
+	                               { NULL, 0, NULL, 0 } };
+
+[[noreturn]] void die(const std::string& msg)
+{
+	std::cerr << PROGRAM ": " << msg << std::endl;
+	exit(EXIT_FAILURE);
+}
+
+void assert_readable(const std::string& path)
+{
+	if (access(path.c_str(), R_OK) == -1) {
+		std::cerr << "error: `" << path << "': " << strerror(errno) << std::endl;
+		exit(EXIT_FAILURE);
+	}
+}
+
+const char* maybeNA(const std::string& s)
+{
+	return s.empty() ? "NA" : s.c_str();
+}
+
+std::string stamp()
+{
+	std::time_t t;
+	time(&t);
+	return ctime(&t);
+}
+
+double now()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- small restatements of the reference's helpers -------------------------------------------
+
+// stripReadNum (Arcs.cpp:243-254)
+void strip_read_num(std::string& name)
+{
+	size_t pos = name.rfind('/');
+	if (pos == std::string::npos || pos == 0 || pos == name.length() - 1)
+		return;
+	if (!std::isdigit((unsigned char)name[pos + 1]))
+		return;
+	name.resize(pos);
+}
+
+// barcode = text after the first "BX:Z:" up to the next ' ' (Arcs.cpp:1227-1251)
+void extract_bx(const std::string& comment, std::string& barcode)
+{
+	barcode.clear();
+	size_t tag = comment.find("BX:Z:");
+	if (tag == std::string::npos)
+		return;
+	size_t end = comment.find(' ', tag);
+	if (end != std::string::npos)
+		barcode.assign(comment, tag + 5, end - tag - 5);
+	else
+		barcode.assign(comment, tag + 5, std::string::npos);
+}
+
+// readFof (Arcs.cpp:776-794): one file name per whitespace-separated token
+std::vector<std::string> read_fof(const std::string& fof)
+{
+	std::vector<std::string> out;
+	if (fof.empty())
+		return out;
+	std::ifstream in(fof.c_str());
+	if (!in)
+		die("error: could not open `" + fof + "'");
+	std::string tok;
+	while (in >> tok)
+		out.push_back(tok);
+	return out;
+}
+
+// checkSameFormat (Arcs.cpp:336-361)
+bool check_same_format(const std::vector<std::string>& files, bool& all_alignment)
+{
+	int prev = 0, cur = 0;
+	for (const auto& f : files) {
+		cur = 0;
+		if (f.find(".sam") != std::string::npos || f.find(".bam") != std::string::npos)
+			cur = 1;
+		if (f.find(".fastq") != std::string::npos || f.find(".fq") != std::string::npos)
+			cur = 2;
+		if (!cur) {
+			std::cout << "Unknown type file is observed!" << std::endl;
+			return false;
+		}
+		if (prev && prev != cur)
+			return false;
+		prev = cur;
+	}
+	all_alignment = (cur == 1);
+	return true;
+}
+
+// normalEstimation / checkSignificance (Arcs.cpp:833-839,1459-1467), same types as the reference
+float normal_estimation(int x, float p, int n)
+{
+	float mean = n * p;
+	float sd = std::sqrt(n * p * (1 - p));
+	return 0.5 * (1 + std::erf((x - mean) / (sd * std::sqrt(2))));
+}
+
+bool check_significance(int max, int second)
+{
+	if (max < params.min_links)
+		return false;
+	float cdf = normal_estimation(max, 0.5, second);
+	return (1 - cdf < params.error_percent);
+}
+
+// ---- barcodes ----------------------------------------------------------------------------------
+struct Barcodes
+{
+	std::unordered_map<std::string, uint32_t> id;
+	std::vector<std::string> name;
+	std::vector<int32_t> mult;    // indexMultMap value
+	std::vector<uint8_t> counted; // the barcode is a key of indexMultMap
+	uint32_t intern(const std::string& b)
+	{
+		auto it = id.find(b);
+		if (it != id.end())
+			return it->second;
+		uint32_t i = (uint32_t)name.size();
+		id.emplace(b, i);
+		name.push_back(b);
+		mult.push_back(0);
+		counted.push_back(0);
+		return i;
+	}
+};
+
+// createIndexMultMap (Arcs.cpp:392-448)
+void load_multfile(const std::string& path, Barcodes& bc)
+{
+	const bool tsv = path.find(".tsv") != std::string::npos;
+	std::ifstream in(path.c_str());
+	if (!in) {
+		std::cerr << "Could not open " << path << ". --fatal.\n";
+		exit(EXIT_FAILURE);
+	}
+	std::string line;
+	size_t n = 0;
+	while (getline(in, line)) {
+		std::string barcode, ms;
+		if (tsv) {
+			std::stringstream ss(line);
+			ss >> barcode >> ms;
+		} else {
+			std::istringstream iss(line);
+			getline(iss, barcode, ',');
+			iss >> ms;
+		}
+		n++;
+		int m = std::stoi(ms);
+		if (!barcode.empty()) {
+			uint32_t i = bc.intern(barcode);
+			bc.mult[i] = m;
+			bc.counted[i] = 1;
+		} else {
+			std::cout << "Please check your multiplicity file." << std::endl;
+		}
+	}
+	if (params.verbose)
+		std::cout << "Saw " << n << "  distinct barcodes." << std::endl;
+}
+
+// readBarcodes' counting rule for one record (Arcs.cpp:514-537): call for every record of a
+// file until the first one with l <= 0
+void count_barcode(const SeqRecord& r, Barcodes& bc, std::string& scratch)
+{
+	if (r.comment.empty())
+		return;
+	if (r.comment.find("BX:Z:") == std::string::npos)
+		return;
+	extract_bx(r.comment, scratch);
+	uint32_t i = bc.intern(scratch);
+	bc.mult[i]++;
+	bc.counted[i] = 1;
+}
+
+// ---- contigs -----------------------------------------------------------------------------------
+struct Contigs
+{
+	std::vector<std::string> name;           // kept contigs (len >= -z), file order; conreci 2i+1 / 2i+2
+	std::vector<int> length;
+	std::unordered_map<std::string, int> to_length; // ARCS::ContigToLength (iteration order matters for .dist.gv)
+	std::vector<uint32_t> first_of_name;     // index of the first kept contig with the same name
+	size_t total = 0, skipped = 0;
+};
+
+// ---- GPU handles -------------------------------------------------------------------------------
+struct Gpu
+{
+	arks_handle* h = nullptr;
+	// two pinned batches
+	struct Batch
+	{
+		char* bases = nullptr;
+		uint32_t* off = nullptr;
+		uint32_t* bc = nullptr;
+		uint64_t n_bases = 0;
+		uint32_t n_pairs = 0;
+	} batch[2];
+	int cur = 0;
+};
+
+constexpr uint64_t kBatchBases = 256ull << 20;
+constexpr uint32_t kBatchPairs = 1u << 20;
+
+void ck(arks_handle* h, int rc, const char* what)
+{
+	if (rc != ARKS_OK) {
+		std::cerr << PROGRAM ": GPU error in " << what << " (" << rc << "): " << arks_last_error(h) << std::endl;
+		exit(EXIT_FAILURE);
+	}
+}
+
+void flush_batch(Gpu& g)
+{
+	Gpu::Batch& b = g.batch[g.cur];
+	if (b.n_pairs == 0)
+		return;
+	b.off[2 * b.n_pairs] = (uint32_t)b.n_bases;
+	ck(g.h, arks_map_pairs(g.h, b.bases, b.off, b.bc, b.n_pairs, params.j_index, nullptr), "arks_map_pairs");
+	g.cur ^= 1;
+	g.batch[g.cur].n_pairs = 0;
+	g.batch[g.cur].n_bases = 0;
+}
+
+void add_pair(Gpu& g, const std::string& s1, const std::string& s2, uint32_t barcode)
+{
+	if (s1.size() + s2.size() > kBatchBases / 2)
+		die("error: read pair longer than the batch buffer");
+	Gpu::Batch* b = &g.batch[g.cur];
+	if (b->n_pairs >= kBatchPairs || b->n_bases + s1.size() + s2.size() > kBatchBases) {
+		flush_batch(g);
+		b = &g.batch[g.cur];
+	}
+	b->off[2 * b->n_pairs] = (uint32_t)b->n_bases;
+	memcpy(b->bases + b->n_bases, s1.data(), s1.size());
+	b->n_bases += s1.size();
+	b->off[2 * b->n_pairs + 1] = (uint32_t)b->n_bases;
+	memcpy(b->bases + b->n_bases, s2.data(), s2.size());
+	b->n_bases += s2.size();
+	b->bc[b->n_pairs] = barcode;
+	b->n_pairs++;
+}
+
+// ---- graph (createGraph / removeDegreeNodes / write_graphviz without Boost) --------------------
+struct Edge
+{
+	int u, v, orientation, weight;
+};
+struct Graph
+{
+	std::vector<std::string> vid; // vertex -> contig name
+	std::vector<Edge> edges;      // in pmap order
+};
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+	printf("Reading user inputs...\n");
+	bool arcsOnly = false, arksOnly = false, dieflag = false;
+	if (const char* s = getenv("ARKS_GPUS"))
+		params.gpus = atoi(s);
+	for (int c; (c = getopt_long(argc, argv, shortopts, longopts, NULL)) != -1;) {
+		std::istringstream arg(optarg != NULL ? optarg : "");
+		switch (c) {
+		case 'u': arg >> params.multfile; break;
+		case 'k': arg >> params.k_value; arksOnly = true; break;
+		case 'j': arg >> params.j_index; arksOnly = true; break;
+		case 't': arg >> params.threads; arksOnly = true; break;
+		case '?': dieflag = true; break;
+		case 'f': arg >> params.file; break;
+		case 'a': arg >> params.fofName; break;
+		case 'B': arg >> params.dist_bin_size; break;
+		case 's': arg >> params.seq_id; arcsOnly = true; break;
+		case 'c': arg >> params.min_reads; break;
+		case 'P': params.output_pair = true; break;
+		case 'D': params.dist_est = true; break;
+		case 'l': arg >> params.min_links; break;
+		case 'z': arg >> params.min_size; break;
+		case 'b': arg >> params.base_name; break;
+		case 'g': arg >> params.dist_graph_name; break;
+		case OPT_TSV: arg >> params.tsv_name; break;
+		case OPT_GAP: arg >> params.gap; break;
+		case OPT_BARCODE_COUNTS: arg >> params.barcode_counts_name; break;
+		case OPT_SAMPLES_TSV: arg >> params.dist_samples_tsv; break;
+		case OPT_DIST_TSV: arg >> params.dist_tsv; break;
+		case OPT_NO_DIST_EST: params.dist_est = false; break;
+		case OPT_DIST_MEDIAN: params.dist_upper = false; break;
+		case OPT_DIST_UPPER: params.dist_upper = true; break;
+		case OPT_ARKS_METHOD: params.arks = true; break;
+		case OPT_BX: break;
+		case OPT_GPUS: arg >> params.gpus; break;
+		case OPT_TWO_PASS: params.two_pass = true; break;
+		case 'm': {
+			std::string a, b;
+			std::getline(arg, a, '-');
+			std::getline(arg, b);
+			std::stringstream ss;
+			ss << a << "\t" << b;
+			ss >> params.min_mult >> params.max_mult;
+		} break;
+		case 'd': arg >> params.max_degree; break;
+		case 'e': arg >> params.end_length; break;
+		case 'r': arg >> params.error_percent; break;
+		case 'v': ++params.verbose; break;
+		case OPT_HELP: std::cout << USAGE; exit(EXIT_SUCCESS);
+		case OPT_VERSION: std::cout << PROGRAM " " PACKAGE_VERSION "\n"; exit(EXIT_SUCCESS);
+		}
+		if (optarg != NULL && c != 'm' && (!arg.eof() || arg.fail())) {
+			std::cerr << PROGRAM ": invalid option: `-" << (char)c << optarg << "'\n";
+			exit(EXIT_FAILURE);
+		}
+	}
+	if ((params.arks && arcsOnly) || (!params.arks && arksOnly)) {
+		std::cerr << PROGRAM ": error: You specified an option that does not match with method "
+		                     "choosen.\nCheck --help for method specific options.\n";
+		dieflag = true;
+	}
+	std::vector<std::string> filenames(argv + optind, argv + argc);
+	if (params.fofName.empty() && filenames.empty()) {
+		std::cerr << PROGRAM ": error: specify input (SAM/BAM file(s) or chromium reads) or a list of "
+		                     "files with -a option\n";
+		dieflag = true;
+	}
+	bool stdIn = !filenames.empty() && filenames[0] == "/dev/stdin";
+	if (!params.file.empty())
+		assert_readable(params.file);
+	if (!params.fofName.empty())
+		assert_readable(params.fofName);
+	for (const auto& f : filenames)
+		assert_readable(f);
+	for (const auto& f : read_fof(params.fofName))
+		filenames.push_back(f);
+	bool alignmentFiles = false;
+	if (!stdIn && !check_same_format(filenames, alignmentFiles)) {
+		std::cerr << "Input files must be all alignment or all read files." << params.file << ". Exiting... \n";
+		dieflag = true;
+	}
+	if (!stdIn && !(alignmentFiles ^ params.arks)) {
+		std::cerr << "File type must be compatible with the method. (BAM/SAM for ARCS) or (Read "
+		             "file for ARKS (--arks)). Exiting... \n";
+		dieflag = true;
+	}
+	if (!params.arks) {
+		std::cerr << PROGRAM ": error: this build implements the k-mer method only: pass --arks (alignment mode is not "
+		                     "part of the B200 hot path).\n";
+		dieflag = true;
+	}
+	if (params.dist_est) {
+		std::cerr << PROGRAM ": error: -D/--dist_est (distance estimation) is not implemented in this build.\n";
+		dieflag = true;
+	}
+	{
+		std::ifstream g(params.file.c_str());
+		if (!g.good() && params.arks) {
+			std::cerr << "Cannot find [-f] scaffold file which is required for --arks" << params.file << ". Exiting... \n";
+			dieflag = true;
+		}
+	}
+	if (params.k_value < ARKS_MIN_K || params.k_value > ARKS_MAX_K) {
+		std::cerr << PROGRAM ": error: -k must be in [" << ARKS_MIN_K << ", " << ARKS_MAX_K << "] in this build.\n";
+		dieflag = true;
+	}
+	if (params.base_name.empty()) {
+		std::ostringstream fn;
+		fn << params.file << ".scaff"
+		   << "_arks"
+		   << "_c" << params.min_reads << "_k" << params.k_value << "_j" << params.j_index << "_l" << params.min_links << "_d"
+		   << params.max_degree << "_e" << params.end_length << "_r" << params.error_percent;
+		params.base_name = fn.str();
+	}
+	if (params.dist_graph_name.empty())
+		params.dist_graph_name = params.base_name + ".dist.gv";
+	if (params.tsv_name.empty())
+		params.tsv_name = params.base_name + "_main.tsv";
+	if (dieflag) {
+		std::cerr << "Try " << PROGRAM << " --help for more information.\n";
+		exit(EXIT_FAILURE);
+	}
+	if (params.gpus < 1)
+		params.gpus = 1;
+	printf("%s\n", "Finished reading user inputs...entering runArcs()...");
+
+	// ---- runArcs banner (Arcs.cpp:1818-1843)
+	std::cout << "Running: " << PROGRAM << " " << PACKAGE_VERSION << "\nARKS method\n pid " << ::getpid() << "\n -c "
+	          << params.min_reads << "\n -d " << params.max_degree << "\n -e " << params.end_length << "\n -l " << params.min_links
+	          << "\n -m " << params.min_mult << '-' << params.max_mult << "\n -r " << params.error_percent << "\n -v "
+	          << params.verbose << "\n -z " << params.min_size << "\n --gap=" << params.gap << "\n -k " << params.k_value << "\n -j "
+	          << params.j_index << "\n -t " << params.threads << "\n --gpus " << params.gpus << "\n -b "
+	          << maybeNA(params.base_name) << "\n -g " << maybeNA(params.dist_graph_name)
+	          << "\n --barcode-counts=" << maybeNA(params.barcode_counts_name) << "\n --tsv=" << maybeNA(params.tsv_name) << "\n -a "
+	          << maybeNA(params.fofName) << "\n -f " << maybeNA(params.file) << "\n -u " << maybeNA(params.multfile) << '\n';
+	for (const auto& f : filenames)
+		std::cout << ' ' << f << '\n';
+	std::cout.flush();
+	const double t_start = now();
+
+	// ---- barcode multiplicities
+	Barcodes bc;
+	const bool have_multfile = !params.multfile.empty();
+	// `goodmult = mult > min || mult < max` (Arcs.cpp:1267) can only be false for an inverted range
+	const bool need_first_pass = !have_multfile && (params.two_pass || params.min_mult >= params.max_mult);
+	std::cout << "\n=>Preprocessing: Gathering barcode multiplicity information..." << stamp();
+	if (have_multfile) {
+		load_multfile(params.multfile, bc);
+	} else if (need_first_pass) {
+		// readBarcodes (Arcs.cpp:481-547)
+		std::string scratch;
+		for (const auto& f : filenames) {
+			SeqReader rd(f);
+			if (!rd.ok()) {
+				std::cerr << "File " << f << " cannot be opened." << std::endl;
+				exit(1);
+			}
+			SeqRecord r;
+			while (rd.read(r) > 0) {
+				r.truncate_at_nul();
+				count_barcode(r, bc, scratch);
+			}
+		}
+		if (params.verbose)
+			std::cout << "Saw " << bc.name.size() << " distinct barcode." << std::endl;
+	} else {
+		std::cout << "Multiplicity information is being formed from reads while they are mapped (single pass)." << std::endl;
+	}
+	const bool mult_known = have_multfile || need_first_pass;
+
+	// ---- contigs: getContigKmers (Arcs.cpp:1021-1129) on the GPU
+	std::cout << "\n=>Preprocessing: Gathering draft information..." << stamp() << "\n";
+	Contigs ct;
+	std::vector<char> end_bases;
+	std::vector<uint64_t> end_off(1, 0);
+	std::vector<uint32_t> end_conreci;
+	{
+		SeqReader rd(params.file);
+		if (!rd.ok())
+			die("error: cannot open " + params.file);
+		SeqRecord r;
+		std::unordered_map<std::string, uint32_t> first;
+		while (rd.read(r) >= 0) {
+			ct.total++;
+			r.truncate_at_nul();
+			const int len = (int)r.seq.size();
+			if (len < params.min_size) {
+				ct.skipped++;
+				continue;
+			}
+			const uint32_t i = (uint32_t)ct.name.size();
+			ct.name.push_back(r.name);
+			ct.length.push_back(len);
+			ct.to_length[r.name] = len;
+			auto it = first.find(r.name);
+			ct.first_of_name.push_back(it == first.end() ? i : it->second);
+			if (it == first.end())
+				first.emplace(r.name, i);
+			int cut = params.end_length;
+			if (cut == 0 || len <= cut * 2)
+				cut = len / 2;
+			end_bases.insert(end_bases.end(), r.seq.begin(), r.seq.begin() + cut);
+			end_off.push_back(end_bases.size());
+			end_conreci.push_back(2 * i + 1);
+			end_bases.insert(end_bases.end(), r.seq.end() - cut, r.seq.end());
+			end_off.push_back(end_bases.size());
+			end_conreci.push_back(2 * i + 2);
+		}
+	}
+	if (params.verbose)
+		std::cerr << "Number of contigs:" << ct.name.size() << "\nSize of Contig Array:" << ct.name.size() * 2 + 1 << std::endl;
+
+	std::cout << "\n=>Storing Kmers from Contig ends... " << stamp() << std::endl;
+	std::vector<Gpu> gpus(params.gpus);
+	arks_index_stats ist{};
+	const double t_index0 = now();
+	for (int d = 0; d < params.gpus; ++d) {
+		Gpu& g = gpus[d];
+		// ARKS_GPUS_SAME_DEVICE=1 (tests): every shard on device 0
+		const int dev = getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d;
+		int rc = arks_create(dev, params.k_value, end_bases.size() + 64, &g.h);
+		if (rc != ARKS_OK)
+			die(std::string("error: cannot initialise GPU ") + std::to_string(d) + ": " + arks_last_error(nullptr));
+		if (!end_conreci.empty())
+			ck(g.h, arks_index_add(g.h, end_bases.data(), end_off.data(), end_conreci.data(), (uint32_t)end_conreci.size()),
+			    "arks_index_add");
+		ck(g.h, arks_index_finalize(g.h, &ist), "arks_index_finalize");
+		// hits on a contig whose name occurred earlier are tallied under the first one (imap is keyed by name)
+		std::vector<uint32_t> remap(2 * ct.name.size() + 1, 0);
+		bool any = false;
+		for (uint32_t i = 0; i < ct.name.size(); ++i) {
+			remap[2 * i + 1] = 2 * ct.first_of_name[i] + 1;
+			remap[2 * i + 2] = 2 * ct.first_of_name[i] + 2;
+			any |= ct.first_of_name[i] != i;
+		}
+		if (any)
+			ck(g.h, arks_set_conreci_remap(g.h, remap.data(), (uint32_t)remap.size()), "arks_set_conreci_remap");
+		for (auto& b : g.batch) {
+			void* p;
+			if (arks_host_alloc(&p, kBatchBases + 64) != ARKS_OK)
+				die("error: cannot allocate pinned host memory");
+			b.bases = (char*)p;
+			if (arks_host_alloc(&p, (2ull * kBatchPairs + 1) * 4) != ARKS_OK)
+				die("error: cannot allocate pinned host memory");
+			b.off = (uint32_t*)p;
+			if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
+				die("error: cannot allocate pinned host memory");
+			b.bc = (uint32_t*)p;
+		}
+	}
+	const double t_index1 = now();
+	end_bases.clear();
+	end_bases.shrink_to_fit();
+	if (params.verbose)
+		printf("%s %zu\n%s %zu\n%s %zu\n%s %llu\n%s %llu\n%s %llu\n%s %llu\n%s %llu\n%s %llu\n",
+		    "Total number of contigs in draft genome: ", ct.total, "Total valid contigs: ", ct.name.size(),
+		    "Total skipped contigs: ", ct.skipped, "Total number of Kmers: ", (unsigned long long)ist.kmers_valid,
+		    "Number Null Kmers: ", (unsigned long long)ist.kmers_null, "Number Kmers Recorded: ", (unsigned long long)ist.recorded,
+		    "Number Kmer Collisions: ", (unsigned long long)ist.collisions,
+		    "Number Times Kmers Removed (since duplicate in different contig): ", (unsigned long long)ist.removed,
+		    "Number of unique kmers (only one contig): ", (unsigned long long)ist.unique);
+
+	// ---- reads: chromiumRead (Arcs.cpp:1132-1351)
+	std::cout << "\n=>Reading Chromium FASTQ file(s)... " << stamp() << std::endl;
+	const double t_map0 = now();
+	size_t skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0, count = 0;
+	{
+		SeqRecord r1, r2;
+		std::string b1, b2, n1, n2, scratch;
+		for (const auto& f : filenames) {
+			if (params.verbose)
+				std::cout << "Reading chrom " << f << std::endl;
+			SeqReader rd(f);
+			if (!rd.ok()) {
+				std::cerr << "File " << f << " cannot be opened." << std::endl;
+				exit(1);
+			} else {
+				std::cerr << "File " << f << " opened." << std::endl;
+			}
+			bool counting = !mult_known; // readBarcodes stops at the first record with l <= 0
+			bool stop = false;
+			while (!stop) {
+				bool paired = false;
+				r1.name.clear();
+				r2.name.clear();
+				r1.comment.clear();
+				r2.comment.clear();
+				int l = rd.read(r1);
+				if (l >= 0) {
+					r1.truncate_at_nul();
+					if (counting) {
+						if (l > 0)
+							count_barcode(r1, bc, scratch);
+						else
+							counting = false;
+					}
+					l = rd.read(r2);
+					if (l >= 0) {
+						r2.truncate_at_nul();
+						if (counting) {
+							if (l > 0)
+								count_barcode(r2, bc, scratch);
+							else
+								counting = false;
+						}
+					} else {
+						r2.name.clear();
+						r2.comment.clear();
+						stop = true;
+					}
+				} else {
+					stop = true;
+				}
+				n1 = r1.name;
+				n2 = stop && l < 0 && r2.name.empty() ? std::string() : r2.name;
+				strip_read_num(n1);
+				strip_read_num(n2);
+				if (n1 == n2) {
+					paired = true;
+				} else {
+					std::cout << "File contains unpaired reads: " << n1 << " " << n2 << std::endl;
+					skipped_unpaired++;
+				}
+				count += 2;
+				if (params.verbose && count % 10000000 == 0)
+					std::cout << "Processed " << count << " read pairs." << std::endl;
+				if (stop)
+					break;
+				extract_bx(r1.comment, b1);
+				extract_bx(r2.comment, b2);
+				if (b1.empty() || b2.empty()) {
+					emptybarcode++;
+					continue;
+				}
+				if (!paired || b1 != b2) {
+					// (the reference still looks barcode1 up here, only to count invalid barcodes)
+					continue;
+				}
+				uint32_t id;
+				if (mult_known) {
+					auto it = bc.id.find(b1);
+					if (it == bc.id.end() || !bc.counted[it->second]) {
+						invalidbarcode++;
+						continue;
+					}
+					id = it->second;
+					const int m = bc.mult[id];
+					if (!(m > params.min_mult || m < params.max_mult)) { // goodmult, Arcs.cpp:1267
+						skipped_badmult++;
+						continue;
+					}
+				} else {
+					id = bc.intern(b1); // validity (is it a key of indexMultMap) is settled after the pass
+				}
+				add_pair(gpus[id % params.gpus], r1.seq, r2.seq, id);
+			}
+		}
+		for (auto& g : gpus)
+			flush_batch(g);
+	}
+	arks_map_stats mst{};
+	for (auto& g : gpus) {
+		arks_map_stats s{};
+		ck(g.h, arks_map_get_stats(g.h, &s), "arks_map_get_stats");
+		uint64_t* a = reinterpret_cast<uint64_t*>(&mst);
+		const uint64_t* b = reinterpret_cast<const uint64_t*>(&s);
+		for (size_t i = 0; i < sizeof(mst) / 8; ++i)
+			a[i] += b[i];
+	}
+	const double t_map1 = now();
+	if (params.verbose) {
+		printf("Stored read pairs: %llu\nSkipped invalid read pairs: %llu\nSkipped unpaired reads: %zu\nSkipped reads pairs without a "
+		       "good contig: %llu\n",
+		    (unsigned long long)mst.pairs_stored, (unsigned long long)(mst.pairs_invalid + skipped_badmult), skipped_unpaired,
+		    (unsigned long long)(mst.pairs_nogood + skipped_badmult));
+		printf("Total valid kmers: %llu\nNumber invalid kmers: %llu\nNumber of kmers found in ContigKmap: %llu\nNumber of kmers "
+		       "recorded in Ktrack: %llu\nNumber of kmers found in ContigKmap but duplicate: %llu\nNumber of reads passing jaccard "
+		       "threshold: %llu\nNumber of reads failing jaccard threshold: %llu\n",
+		    (unsigned long long)mst.kmers_valid, (unsigned long long)mst.kmers_invalid, (unsigned long long)mst.found,
+		    (unsigned long long)mst.recorded, (unsigned long long)mst.dups, (unsigned long long)mst.reads_pass,
+		    (unsigned long long)mst.reads_fail);
+		if (emptybarcode > 0)
+			printf("WARNING:: Your chromium read file has %zu readpairs that have an empty barcode.", emptybarcode);
+		if (invalidbarcode > 0)
+			printf("WARNING:: Your chromium read file has %zu read pairs that have barcodes not in the barcode multiplicity file.",
+			    invalidbarcode);
+		const double kmers = (double)(mst.kmers_valid + mst.kmers_invalid);
+		printf("GPU mapping: %.3f s wall (parse + H2D + kernels), %.3e read k-mers/s end to end; index build %.3f s\n", t_map1 - t_map0,
+		    kmers / std::max(1e-9, t_map1 - t_map0), t_index1 - t_index0);
+	}
+
+	// ---- pairContigs (Arcs.cpp:1378-1435) on the GPU
+	std::cout << "\n=> Pairing scaffolds... " << stamp();
+	const uint32_t n_bc = (uint32_t)bc.name.size();
+	std::vector<int32_t> mult(n_bc);
+	for (uint32_t i = 0; i < n_bc; ++i)
+		mult[i] = bc.counted[i] ? bc.mult[i] : INT32_MIN; // a barcode that is not a key of indexMultMap never had its pairs stored
+	// rank of contig names under std::string '<' (PairMap's key order)
+	const uint32_t n_ct = (uint32_t)ct.name.size();
+	std::vector<uint32_t> order(n_ct), lexrank(n_ct);
+	for (uint32_t i = 0; i < n_ct; ++i)
+		order[i] = i;
+	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ct.name[a] < ct.name[b] || (ct.name[a] == ct.name[b] && a < b); });
+	for (uint32_t r = 0, rank = 0; r < n_ct; ++r) {
+		if (r > 0 && ct.name[order[r]] != ct.name[order[r - 1]])
+			rank = r;
+		lexrank[order[r]] = rank;
+	}
+	struct PairRow
+	{
+		uint32_t a, b, c[4];
+	};
+	std::vector<PairRow> pmap;
+	// imap rows (for the TSV): barcode, contig, head, tail
+	std::vector<uint32_t> im_bc, im_ct, im_h, im_t;
+	for (int d = 0; d < params.gpus; ++d) {
+		Gpu& g = gpus[d];
+		uint64_t n_rows = 0;
+		ck(g.h, arks_imap_size(g.h, &n_rows), "arks_imap_size");
+		const size_t base = im_bc.size();
+		im_bc.resize(base + n_rows);
+		im_ct.resize(base + n_rows);
+		im_h.resize(base + n_rows);
+		im_t.resize(base + n_rows);
+		if (n_rows)
+			ck(g.h, arks_imap_export(g.h, im_bc.data() + base, im_ct.data() + base, im_h.data() + base, im_t.data() + base, n_rows, &n_rows),
+			    "arks_imap_export");
+		ck(g.h, arks_pair_links(g.h, mult.data(), n_bc, params.min_mult, params.max_mult, params.min_reads, params.error_percent,
+		            lexrank.data(), n_ct),
+		    "arks_pair_links");
+		uint64_t n = 0;
+		ck(g.h, arks_pmap_size(g.h, &n), "arks_pmap_size");
+		std::vector<uint32_t> a(n), b(n), c(4 * n);
+		if (n)
+			ck(g.h, arks_pmap_export(g.h, a.data(), b.data(), c.data(), n, &n), "arks_pmap_export");
+		for (uint64_t i = 0; i < n; ++i)
+			pmap.push_back(PairRow{ a[i], b[i], { c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3] } });
+	}
+	if (params.gpus > 1) {
+		// barcodes are disjoint across GPUs, so the link maps simply add up
+		std::sort(pmap.begin(), pmap.end(), [&](const PairRow& x, const PairRow& y) {
+			return std::make_pair(lexrank[x.a], lexrank[x.b]) < std::make_pair(lexrank[y.a], lexrank[y.b]);
+		});
+		size_t w = 0;
+		for (size_t i = 0; i < pmap.size(); ++i) {
+			if (w && pmap[w - 1].a == pmap[i].a && pmap[w - 1].b == pmap[i].b) {
+				for (int o = 0; o < 4; ++o)
+					pmap[w - 1].c[o] += pmap[i].c[o];
+			} else {
+				pmap[w++] = pmap[i];
+			}
+		}
+		pmap.resize(w);
+	}
+	// drop imap rows of barcodes that are not keys of indexMultMap (their pairs were never stored)
+	{
+		size_t w = 0;
+		for (size_t i = 0; i < im_bc.size(); ++i)
+			if (bc.counted[im_bc[i]]) {
+				im_bc[w] = im_bc[i];
+				im_ct[w] = im_ct[i];
+				im_h[w] = im_h[i];
+				im_t[w] = im_t[i];
+				w++;
+			}
+		im_bc.resize(w);
+		im_ct.resize(w);
+		im_h.resize(w);
+		im_t.resize(w);
+	}
+
+	// ARKS_DUMP_IMAP=FILE: the IndexMap as text, one "barcode contig H|T count" line per entry (both ends of
+	// every contig a barcode touches, as after the zero-fill of Arcs.cpp:1309-1319), sorted -- for parity tests
+	if (const char* dump = getenv("ARKS_DUMP_IMAP")) {
+		std::vector<std::string> lines;
+		for (size_t i = 0; i < im_bc.size(); ++i) {
+			lines.push_back(bc.name[im_bc[i]] + "\t" + ct.name[im_ct[i]] + "\tH\t" + std::to_string(im_h[i]));
+			lines.push_back(bc.name[im_bc[i]] + "\t" + ct.name[im_ct[i]] + "\tT\t" + std::to_string(im_t[i]));
+		}
+		std::sort(lines.begin(), lines.end());
+		std::ofstream out(dump);
+		for (const auto& l : lines)
+			out << l << "\n";
+	}
+
+	if (params.output_pair) {
+		std::cout << "\n=> Outputting Pairing information... " << stamp();
+		std::ofstream out((params.base_name + "_pair.tsv").c_str());
+		for (const auto& p : pmap)
+			out << ct.name[p.a] << "\t" << ct.name[p.b] << "\t" << p.c[0] << "\t" << p.c[1] << "\t" << p.c[2] << "\t" << p.c[3] << std::endl;
+	}
+
+	// ---- createGraph (Arcs.cpp:1475-1526)
+	std::cout << "\n=> Creating the graph... " << stamp();
+	Graph g;
+	{
+		std::unordered_map<uint32_t, int> vmap; // by first-of-name contig index
+		for (const auto& p : pmap) {
+			unsigned max = 0, index = 0;
+			for (unsigned i = 0; i < 4; ++i)
+				if (p.c[i] > max) {
+					max = p.c[i];
+					index = i;
+				}
+			unsigned second = 0;
+			for (unsigned i = 0; i < 4; ++i)
+				if (p.c[i] != max && p.c[i] > second)
+					second = p.c[i];
+			if (check_significance((int)max, (int)(max + second))) {
+				for (uint32_t cidx : { p.a, p.b })
+					if (!vmap.count(cidx)) {
+						vmap[cidx] = (int)g.vid.size();
+						g.vid.push_back(ct.name[cidx]);
+					}
+				g.edges.push_back(Edge{ vmap[p.a], vmap[p.b], (int)index, (int)max });
+			}
+		}
+	}
+
+	// ---- writePostRemovalGraph / removeDegreeNodes / writeGraph (Arcs.cpp:1549-1610)
+	std::cout << "\n=> Writing graph file... " << stamp() << "\n";
+	const std::string graphFile = params.base_name + "_original.gv";
+	if (params.max_degree != 0) {
+		std::cout << "      Deleting nodes with degree > " << params.max_degree << "... \n";
+		std::vector<int> deg(g.vid.size(), 0);
+		for (const auto& e : g.edges) {
+			deg[e.u]++;
+			deg[e.v]++;
+		}
+		std::vector<int> remap(g.vid.size(), -1);
+		std::vector<std::string> nv;
+		for (size_t i = 0; i < g.vid.size(); ++i)
+			if (deg[i] <= params.max_degree) {
+				remap[i] = (int)nv.size();
+				nv.push_back(g.vid[i]);
+			}
+		std::vector<Edge> ne;
+		for (const auto& e : g.edges)
+			if (remap[e.u] >= 0 && remap[e.v] >= 0)
+				ne.push_back(Edge{ remap[e.u], remap[e.v], e.orientation, e.weight });
+		g.vid.swap(nv);
+		g.edges.swap(ne);
+	} else {
+		std::cout << "      Max Degree (-d) set to: " << params.max_degree << ". Will not delete any vertices from graph.\n";
+	}
+	std::cout << "      Writing graph file to " << graphFile << "...\n";
+	{
+		std::ofstream out(graphFile.c_str());
+		if (!out)
+			die("error: cannot write " + graphFile);
+		out << "graph G {\n";
+		for (size_t i = 0; i < g.vid.size(); ++i)
+			out << i << " [id=" << g.vid[i] << "];\n";
+		for (const auto& e : g.edges)
+			out << e.u << "--" << e.v << " [label=" << e.orientation << ", weight=" << e.weight << "];\n";
+		out << "}\n";
+	}
+	const double t_gv = now();
+
+	// ---- createAbyssGraph / writeAbyssGraph (Arcs.cpp:1615-1672; Graph/DotIO.h:82-114)
+	std::cout << "\n=> Creating the ABySS graph... " << stamp();
+	std::cout << "\n=> Writing the ABySS graph file... " << stamp() << "\n";
+	{
+		// two vertices per contig ("name+" then "name-") in ContigToLength iteration order; an edge
+		// u -> v also adds its complement v^ -> u^
+		std::vector<std::string> vname;
+		std::vector<int> vlen;
+		std::unordered_map<std::string, size_t> vindex; // contig name -> index of its '+' vertex
+		for (const auto& it : ct.to_length) {
+			vindex[it.first] = vname.size();
+			vname.push_back(it.first + "+");
+			vlen.push_back(it.second);
+			vname.push_back(it.first + "-");
+			vlen.push_back(it.second);
+		}
+		struct Out
+		{
+			size_t to;
+			int n;
+		};
+		std::vector<std::vector<Out>> adj(vname.size());
+		auto has_edge = [&](size_t u, size_t v) {
+			for (const auto& o : adj[u])
+				if (o.to == v)
+					return true;
+			return false;
+		};
+		for (const auto& e : g.edges) {
+			const size_t u = vindex[g.vid[e.u]] + (e.orientation < 2 ? 1 : 0);
+			const size_t v = vindex[g.vid[e.v]] + (e.orientation % 2 ? 1 : 0);
+			if (has_edge(u, v)) {
+				std::cerr << "error: Duplicate edge: \"" << vname[u] << "\" -> \"" << vname[v] << '"' << std::endl;
+				exit(EXIT_FAILURE);
+			}
+			adj[u].push_back(Out{ v, e.weight });
+			const size_t uc = u ^ 1, vc = v ^ 1;
+			if (!(vc == u && uc == v))
+				adj[vc].push_back(Out{ uc, e.weight });
+		}
+		std::ofstream out(params.dist_graph_name.c_str());
+		if (!out)
+			die("error: cannot write " + params.dist_graph_name);
+		out << "digraph arcs {\n";
+		for (size_t i = 0; i < vname.size(); ++i)
+			out << '"' << vname[i] << "\" [l=" << vlen[i] << "]\n";
+		for (size_t u = 0; u < vname.size(); ++u)
+			for (const auto& o : adj[u])
+				out << '"' << vname[u] << "\" -> \"" << vname[o.to] << "\" [d=" << (int)params.gap << " e=" << std::fixed
+				    << std::setprecision(1) << (float)params.gap << " n=" << o.n << "]\n";
+		out << "}\n";
+	}
+
+	// ---- countBarcodes + writeTSV (Arcs.cpp:815-830,1709-1757)
+	if (!params.tsv_name.empty()) {
+		size_t barcodeCount = 0, n_keys = 0;
+		for (uint32_t i = 0; i < n_bc; ++i)
+			if (bc.counted[i]) {
+				n_keys++;
+				if (bc.mult[i] >= params.min_mult && bc.mult[i] <= params.max_mult)
+					++barcodeCount;
+			}
+		std::vector<uint8_t> seen(n_bc, 0);
+		size_t scaffold_end_barcodes = 0;
+		for (uint32_t b : im_bc)
+			if (!seen[b]) {
+				seen[b] = 1;
+				scaffold_end_barcodes++;
+			}
+		std::cout << "{ \"All_barcodes_unfiltered\":" << n_keys << ", \"All_barcodes_filtered\":" << barcodeCount
+		          << ", \"Scaffold_end_barcodes\":" << scaffold_end_barcodes << ", \"Min_barcode_reads_threshold\":" << params.min_mult
+		          << ", \"Max_barcode_reads_threshold\":" << params.max_mult << " }\n";
+		std::cout << "\n=> Writing TSV file... " << stamp();
+		// barcodes per scaffold end with count >= min_reads (a missing end is a zero-count entry, Arcs.cpp:1309-1319)
+		std::vector<unsigned> per_end(2 * (size_t)n_ct, 0); // [2*contig + (head ? 0 : 1)]
+		for (size_t i = 0; i < im_bc.size(); ++i) {
+			if ((int)im_h[i] >= params.min_reads)
+				per_end[2 * (size_t)im_ct[i]]++;
+			if ((int)im_t[i] >= params.min_reads)
+				per_end[2 * (size_t)im_ct[i] + 1]++;
+		}
+		std::ofstream f(params.tsv_name.c_str());
+		if (!f)
+			die("error: cannot write " + params.tsv_name);
+		f << "U\tV\tBest_orientation\tShared_barcodes\tU_barcodes\tV_barcodes\tAll_barcodes\n";
+		for (const auto& p : pmap) {
+			const std::string& u = ct.name[p.a];
+			const std::string& v = ct.name[p.b];
+			unsigned max_counts = *std::max_element(p.c, p.c + 4);
+			for (unsigned i = 0; i < 4; ++i) {
+				if (p.c[i] == 0)
+					continue;
+				const bool usense = i < 2, vsense = i % 2;
+				// barcodes_per_scaffold_end[(u, usense)] / [(v, !vsense)]: bool = isHead
+				const unsigned ub = per_end[2 * (size_t)p.a + (usense ? 0 : 1)];
+				const unsigned vb = per_end[2 * (size_t)p.b + (!vsense ? 0 : 1)];
+				f << u << (usense ? '-' : '+') << '\t' << v << (vsense ? '-' : '+') << '\t' << (p.c[i] == max_counts ? "T" : "F") << '\t'
+				  << p.c[i] << '\t' << ub << '\t' << vb << '\t' << barcodeCount << '\n';
+				f << v << (vsense ? '+' : '-') << '\t' << u << (usense ? '+' : '-') << '\t' << (p.c[i] == max_counts ? "T" : "F") << '\t'
+				  << p.c[i] << '\t' << vb << '\t' << ub << '\t' << barcodeCount << '\n';
+			}
+		}
+	}
+
+	// ---- writeBarcodeCountsTSV (Arcs.cpp:1678-1700)
+	if (!params.barcode_counts_name.empty()) {
+		std::cout << "\n=> Writing reads per barcode TSV file... " << stamp();
+		std::string path = params.barcode_counts_name;
+		if (path.find(".tsv") == std::string::npos)
+			path += ".tsv";
+		std::vector<std::pair<std::string, unsigned>> sorted;
+		for (uint32_t i = 0; i < n_bc; ++i)
+			if (bc.counted[i])
+				sorted.emplace_back(bc.name[i], (unsigned)bc.mult[i]);
+		std::sort(sorted.begin(), sorted.end(), [](const std::pair<std::string, unsigned>& a, const std::pair<std::string, unsigned>& b) {
+			return a.second != b.second ? a.second > b.second : a.first < b.first;
+		});
+		std::ofstream f(path.c_str());
+		if (!f)
+			die("error: cannot write " + path);
+		for (const auto& x : sorted)
+			f << x.first << '\t' << x.second << '\n';
+	}
+	if (params.verbose)
+		printf("wall-clock: start -> _original.gv closed %.3f s (index %.3f s, reads %.3f s)\n", t_gv - t_start, t_index1 - t_index0,
+		    t_map1 - t_map0);
+	for (auto& gp : gpus) {
+		for (auto& b : gp.batch) {
+			arks_host_free(b.bases);
+			arks_host_free(b.off);
+			arks_host_free(b.bc);
+		}
+		arks_destroy(gp.h);
+	}
+	std::cout << "\n=> Done.\n" << stamp();
+	return 0;
+}

@@ -1,0 +1,174 @@
+// seq_reader.h -- streaming FASTA/FASTQ reader over zlib with the record grammar of the
+// reader the reference uses (klib's kseq as vendored in Arcs/kseq.h:175-215), written from
+// that grammar's description, not from its macros:
+//
+//  * between records (at start, or after a FASTQ record) skip bytes until the next '>' or '@';
+//  * name = bytes up to the first isspace(); if that delimiter was not '\n' the rest of the
+//    line is the comment; a trailing '\r' is dropped from a line that has more than one char;
+//  * the sequence is every following line up to a line that STARTS with '>', '@' or '+';
+//    empty lines are skipped;
+//  * '+' starts the quality: skip that line, then append lines until quality is at least as
+//    long as the sequence; a length mismatch is error -2, EOF is -1.
+//
+// Works for plain and gzip input (gzread is transparent for uncompressed files).
+#pragma once
+#include <cctype>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+namespace arks_host {
+
+struct SeqRecord
+{
+	std::string name, comment, seq, qual;
+	// The reference copies name / comment / sequence out of the reader as C strings
+	// (`sequence = seq->seq.s`, Arcs.cpp:1053,1190-1200), so everything from the first NUL byte
+	// on is dropped.  Call after read().
+	void truncate_at_nul()
+	{
+		for (std::string* s : { &name, &comment, &seq }) {
+			size_t z = s->find('\0');
+			if (z != std::string::npos)
+				s->resize(z);
+		}
+	}
+};
+
+class SeqReader
+{
+  public:
+	explicit SeqReader(const std::string& path, size_t bufsize = 1u << 20)
+	  : m_buf(bufsize)
+	{
+		m_fp = gzopen(path.c_str(), "r");
+		if (m_fp)
+			gzbuffer(m_fp, 1u << 18);
+	}
+	~SeqReader()
+	{
+		if (m_fp)
+			gzclose(m_fp);
+	}
+	SeqReader(const SeqReader&) = delete;
+	SeqReader& operator=(const SeqReader&) = delete;
+	bool ok() const { return m_fp != nullptr; }
+
+	// >= 0: sequence length; -1: end of file; -2: truncated / mismatched quality
+	int read(SeqRecord& r)
+	{
+		int c;
+		if (m_last == 0) {
+			while ((c = getc()) != -1 && c != '>' && c != '@') {
+			}
+			if (c == -1)
+				return -1;
+			m_last = c;
+		}
+		r.comment.clear();
+		r.seq.clear();
+		r.qual.clear();
+		int delim = 0;
+		if (!until_space(r.name, &delim))
+			return -1;
+		if (delim != '\n')
+			line(r.comment, false);
+		while ((c = getc()) != -1 && c != '>' && c != '+' && c != '@') {
+			if (c == '\n')
+				continue;
+			r.seq.push_back((char)c);
+			line(r.seq, true);
+		}
+		if (c == '>' || c == '@')
+			m_last = c;
+		if (c != '+')
+			return (int)r.seq.size();
+		while ((c = getc()) != -1 && c != '\n') {
+		}
+		if (c == -1)
+			return -2;
+		while (line(r.qual, true) && r.qual.size() < r.seq.size()) {
+		}
+		m_last = 0;
+		if (r.seq.size() != r.qual.size())
+			return -2;
+		return (int)r.seq.size();
+	}
+
+  private:
+	bool fill()
+	{
+		if (m_eof)
+			return false;
+		m_begin = 0;
+		int n = gzread(m_fp, m_buf.data(), (unsigned)m_buf.size());
+		m_end = n > 0 ? (size_t)n : 0;
+		if (m_end == 0) {
+			m_eof = true;
+			return false;
+		}
+		return true;
+	}
+	int getc()
+	{
+		if (m_begin >= m_end && !fill())
+			return -1;
+		return (unsigned char)m_buf[m_begin++];
+	}
+	// reads up to (not including) the first whitespace byte; false at EOF with nothing read
+	bool until_space(std::string& s, int* delim)
+	{
+		s.clear();
+		*delim = 0;
+		bool got = false;
+		for (;;) {
+			if (m_begin >= m_end && !fill())
+				break;
+			got = true;
+			size_t i = m_begin;
+			while (i < m_end && !isspace((unsigned char)m_buf[i]))
+				++i;
+			s.append(m_buf.data() + m_begin, i - m_begin);
+			m_begin = i + 1;
+			if (i < m_end) {
+				*delim = (unsigned char)m_buf[i];
+				break;
+			}
+		}
+		return got;
+	}
+	// appends the rest of the current line; false at EOF with nothing read.  As in the
+	// reference's reader the '\r' test looks at the whole accumulated string.
+	bool line(std::string& s, bool append)
+	{
+		if (!append)
+			s.clear();
+		bool got = false;
+		for (;;) {
+			if (m_begin >= m_end && !fill())
+				break;
+			got = true;
+			const char* p = m_buf.data() + m_begin;
+			const char* nl = (const char*)memchr(p, '\n', m_end - m_begin);
+			size_t n = nl ? (size_t)(nl - p) : m_end - m_begin;
+			s.append(p, n);
+			m_begin += n + 1;
+			if (nl)
+				break;
+		}
+		if (!got)
+			return false;
+		if (s.size() > 1 && s.back() == '\r')
+			s.pop_back();
+		return true;
+	}
+
+	gzFile m_fp = nullptr;
+	std::vector<char> m_buf;
+	size_t m_begin = 0, m_end = 0;
+	bool m_eof = false;
+	int m_last = 0;
+};
+
+} // namespace arks_host

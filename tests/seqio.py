@@ -35,7 +35,7 @@ def read_fastq(path):
             h = f.readline()
             if not h:
                 break
-            s = f.readline().rstrip(b"\r\n")
+            s = f.readline().rstrip(b"\r\n").split(b"\0")[0]  # the reference keeps C strings: cut at a NUL
             f.readline()
             f.readline()
             h = h.rstrip(b"\r\n")[1:]

@@ -1,0 +1,109 @@
+"""The `arcs --arks` drop-in command line (arcs_b200/bin/arcs) against
+ - the reference's golden demo outputs (Examples/arks_test-demo, arks-long_test-demo) and
+ - outputs of the reference's own code (oracle/_ref/arcs_ref) on adversarial inputs, committed under
+   tests/golden/cli_cases by tools/make_fixtures.py.
+Byte-for-byte on _original.gv, _main.tsv, barcode counts and the pair map."""
+import glob
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+ARCS = os.path.join(ROOT, "arcs_b200", "bin", "arcs")
+
+
+def run_arcs(args, cwd):
+    p = subprocess.run([ARCS] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def read(path):
+    with open(path) as f:
+        return f.read()
+
+
+def test_arks_demo_cli(tmp_path):
+    d = os.path.join(GOLD, "arks_demo")
+    out = run_arcs(["--arks", "-v", "-f", os.path.join(d, "test_scaffolds.renamed.fa"), "-c", "5", "-m", "50-6000", "-r", "0.05",
+                    "-e", "30000", "-z", "500", "-j", "0.55", "-k", "30", "-t", "8", "-d", "0", "--gap", "100", "-b",
+                    str(tmp_path / "demo"), os.path.join(d, "test_reads.fq.gz"), "--barcode-counts", str(tmp_path / "bc.tsv")],
+                   tmp_path)
+    assert read(tmp_path / "demo_original.gv") == read(os.path.join(d, "expected_original.gv"))
+    # verbose counters of the golden log
+    for line in ["Total number of Kmers:  123190", "Number Null Kmers:  303", "Number Kmers Recorded:  118710",
+                 "Number Kmer Collisions:  4480", "Number Times Kmers Removed (since duplicate in different contig):  547",
+                 "Number of unique kmers (only one contig):  118334", "Stored read pairs: 21632",
+                 "Skipped reads pairs without a good contig: 6012", "Total valid kmers: 6109324",
+                 "Number of kmers found in ContigKmap: 4862376", "Number of kmers recorded in Ktrack: 4814099",
+                 "Number of kmers found in ContigKmap but duplicate: 48277", "Number of reads passing jaccard threshold: 44503",
+                 "Number of reads failing jaccard threshold: 10785"]:
+        assert line in out, line
+    assert os.path.exists(tmp_path / "demo.dist.gv") and os.path.exists(tmp_path / "demo_main.tsv")
+    assert len(read(tmp_path / "bc.tsv").splitlines()) == 1085
+
+
+def test_arks_long_demo_cli(tmp_path):
+    d = os.path.join(GOLD, "arks_long_demo")
+    run_arcs(["--arks", "-v", "-f", os.path.join(d, "test_scaffolds.renamed.fa"), "-c", "3", "-m", "8-10000", "-r", "0.05", "-e",
+              "30000", "-z", "500", "-j", "0.05", "-k", "20", "-t", "8", "-d", "0", "--gap", "100", "-b", str(tmp_path / "long"),
+              "-u", os.path.join(d, "barcodeMultiplicityArcs.tsv"), os.path.join(d, "test_reads.cut250.fq.gz")], tmp_path)
+    assert read(tmp_path / "long_original.gv") == read(os.path.join(d, "expected_original.gv"))
+    assert read(tmp_path / "long_main.tsv") == read(os.path.join(d, "expected_main.tsv"))
+    # .dist.gv lists vertices in the iteration order of a std::unordered_map<std::string,int>
+    # (Arcs.cpp:1622), which depends on the libstdc++ build: with this image's g++ 13 the reference
+    # itself gives "2 3 1", the golden (older toolchain) "3 2 1".  Same lines, order aside:
+    got = read(tmp_path / "long.dist.gv").splitlines()
+    want = read(os.path.join(d, "expected.dist.gv")).splitlines()
+    assert got[0] == want[0] == "digraph arcs {" and got[-1] == want[-1] == "}"
+    assert sorted(got) == sorted(want)
+    nv = sum(1 for x in want if " -> " not in x and x.startswith('"'))
+    assert all(" -> " not in x for x in got[1:1 + nv]) and all(" -> " in x for x in got[1 + nv:-1])
+
+
+def test_arks_long_demo_stdin(tmp_path):
+    """arcs-make's arks-long rule pipes reads into /dev/stdin with -u (bin/arcs-make:302-313)"""
+    d = os.path.join(GOLD, "arks_long_demo")
+    cmd = ("zcat %s | %s --arks -f %s -c 3 -m 8-10000 -r 0.05 -e 30000 -z 500 -j 0.05 -k 20 -b %s -u %s /dev/stdin"
+           % (os.path.join(d, "test_reads.cut250.fq.gz"), ARCS, os.path.join(d, "test_scaffolds.renamed.fa"), tmp_path / "s",
+              os.path.join(d, "barcodeMultiplicityArcs.tsv")))
+    subprocess.run(cmd, shell=True, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+    assert read(tmp_path / "s_original.gv") == read(os.path.join(d, "expected_original.gv"))
+
+
+CASES = sorted(glob.glob(os.path.join(GOLD, "cli_cases", "*", "expected_*_args.json")))
+
+
+@pytest.mark.parametrize("argsfile", CASES, ids=[os.path.relpath(c, os.path.join(GOLD, "cli_cases")) for c in CASES])
+@pytest.mark.parametrize("mode", ["one-pass", "two-pass", "2gpu-ids"])
+def test_cli_matches_reference_code(argsfile, mode, tmp_path):
+    d = os.path.dirname(argsfile)
+    tag = os.path.basename(argsfile)[len("expected_"):-len("_args.json")]
+    spec = json.load(open(argsfile))
+    exp = os.path.join(d, "expected_" + tag)
+    args = ["--arks", "-f", os.path.join(d, "draft.fa"), "-b", str(tmp_path / "o"), "--barcode-counts", str(tmp_path / "bc.tsv"),
+            "-P"] + spec["args"]
+    if spec["multfile"]:
+        args += ["-u", os.path.join(d, spec["multfile"])]
+    if mode == "two-pass":
+        args.append("--two-pass")
+    env_gpus = None
+    if mode == "2gpu-ids":
+        # exercises the barcode-sharded multi-handle path; with one physical GPU both shards land on device 0
+        env_gpus = "2"
+    args.append(os.path.join(d, "reads.fq.gz"))
+    env = dict(os.environ)
+    if env_gpus:
+        env["ARKS_GPUS"] = env_gpus
+        env["ARKS_GPUS_SAME_DEVICE"] = "1"
+    p = subprocess.run([ARCS] + args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert read(tmp_path / "o_original.gv") == read(exp + "_original.gv")
+    assert read(tmp_path / "o_main.tsv") == read(exp + "_main.tsv")
+    assert read(tmp_path / "o_pair.tsv") == read(exp + "_pmap.txt")
+    assert read(tmp_path / "bc.tsv") == read(exp + "_bc.tsv")

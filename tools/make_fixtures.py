@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Generates tests/golden/cli_cases/: small adversarial FASTA/FASTQ inputs plus the outputs of the
+reference's own hot-path code (oracle/_ref/arcs_ref) on them.  Run here (needs /root/reference to have
+built oracle/_ref); the fixtures are committed so the GPU box does not need the reference.
+
+  python tools/make_fixtures.py
+"""
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tools import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "cli_cases")
+REF = os.path.join(ROOT, "oracle", "_ref", "arcs_ref")
+
+
+def wrap(seq, width):
+    return "\n".join(seq[i:i + width] for i in range(0, len(seq), width))
+
+
+def make_case(name, seed, k, contig_names=None, fastq_mutator=None, genome_len=90000, mean_contig=9000,
+              n_barcodes=50, ppb=40, read_len=150, jitter=30, mol_len=25000, mols=2):
+    rng = np.random.default_rng(seed)
+    genome, contigs = synth.make_draft(rng, genome_len, mean_contig, k, n_runs=8, palindromes=4, iupac=4)
+    d = os.path.join(OUT, name)
+    os.makedirs(d, exist_ok=True)
+    # FASTA: multi-line, some CRLF, some lower case, comments, a contig shorter than -z, duplicate names
+    with open(os.path.join(d, "draft.fa"), "w", newline="") as f:
+        for i, (cname, s, e) in enumerate(contigs):
+            nm = contig_names[i] if contig_names and i < len(contig_names) else cname
+            seq = genome[s:e].tobytes().decode()
+            eol = "\r\n" if i % 4 == 1 else "\n"
+            f.write(">%s some comment%s" % (nm, eol))
+            f.write(wrap(seq, 70 if i % 2 else 10 ** 9).replace("\n", eol) + eol)
+            if i % 3 == 0:
+                f.write(eol)
+        f.write(">tiny\nACGTACGTACGTACGTACGT\n")
+    rb, roff, bc = synth.make_reads(rng, genome, n_barcodes=n_barcodes, pairs_per_barcode=ppb, read_len=read_len,
+                                    mol_len=mol_len, mols_per_barcode=mols, sub_rate=0.003, n_rate=0.002, len_jitter=jitter)
+    recs = []
+    for p in range(len(bc)):
+        code = "".join("ACGT"[(int(bc[p]) >> (2 * (7 - q))) & 3] for q in range(8)) + "-1"
+        for m in range(2):
+            s = rb[roff[2 * p + m]:roff[2 * p + m + 1]].tobytes().decode()
+            recs.append(["r%d/%d" % (p, m + 1), "BX:Z:%s" % code, s, "I" * len(s)])
+    if fastq_mutator:
+        recs = fastq_mutator(recs, rng)
+    with gzip.open(os.path.join(d, "reads.fq.gz"), "wt", newline="") as f:
+        for nm, cm, s, q in recs:
+            f.write("@%s%s\n%s\n+\n%s\n" % (nm, (" " + cm) if cm is not None else "", s, q))
+    return d
+
+
+def mutate(recs, rng):
+    n = len(recs)
+    out = []
+    for i in range(0, n, 2):
+        a, b = list(recs[i]), list(recs[i + 1])
+        t = (i // 2) % 29
+        if t == 1:
+            a[1] = None  # no comment at all
+        elif t == 2:
+            b[1] = "RG:Z:x"  # no BX on mate 2
+        elif t == 3:
+            b[1] = b[1].replace("-1", "-2")  # barcodes differ
+        elif t == 4:
+            a[0], b[0] = "q%d" % i, "w%d" % i  # unpaired names
+        elif t == 5:
+            a[1] = "XY:Z:1 " + a[1] + " ZZ:i:3"  # BX in the middle, space terminated
+            b[1] = "XY:Z:1 " + b[1] + " ZZ:i:3"
+        elif t == 6:
+            a[1] = a[1] + "\tQT:Z:x"  # a tab does not terminate the barcode
+        elif t == 7:
+            a[0], b[0] = "name%d" % i, "name%d" % i  # no /1 /2 suffix
+        elif t == 8:
+            a[2] = a[2][:10]  # shorter than k
+            a[3] = a[3][:10]
+        elif t == 9:
+            a[2] = a[2][:40] + "NNNNNNNN" + a[2][48:]  # too many N: invalid pair
+        elif t == 10:
+            a[2] = a[2][:30] + "R" + a[2][31:]  # IUPAC in a read: invalid pair
+        elif t == 11:
+            a[2] = a[2].lower()
+        elif t == 12:
+            a[1] = "BX:Z:"  # empty barcode
+            b[1] = "BX:Z:"
+        elif t == 13:
+            a[0] = a[0].replace("/1", "/1x")  # "/" followed by a digit: suffix stripped from there
+        out += [a, b]
+    # an odd trailing record is dropped by the reference
+    out.append(["tail/1", "BX:Z:AAAAAAAA-1", "ACGTACGTACGTACGTACGTACGTACGTACGT", "I" * 32])
+    return out
+
+
+def run_ref(d, args, tag, multfile=None):
+    base = os.path.join(d, "expected_" + tag)
+    cmd = [REF, "-f", os.path.join(d, "draft.fa"), "-b", base, "--tsv", base + "_main.tsv", "--barcode-counts", base + "_bc.tsv",
+           "--dump-imap", base + "_imap.txt", "--dump-pmap", base + "_pmap.txt", "--timing-json", base + "_stats.json"] + args
+    if multfile:
+        cmd += ["-u", multfile]
+    cmd.append(os.path.join(d, "reads.fq.gz"))
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    json.dump({"args": args, "multfile": os.path.basename(multfile) if multfile else None}, open(base + "_args.json", "w"))
+
+
+def main():
+    if not os.path.exists(REF):
+        raise SystemExit("oracle/_ref/arcs_ref is missing: run oracle/build_ref.sh where /root/reference exists")
+    # case A: k=30 defaults-ish, adversarial FASTQ, contig names whose string order differs from numeric order
+    names = ["10", "9", "100", "2", "b", "a", "2", "11", "1", "3"]  # "2" appears twice
+    d = make_case("mixed_k30", 11, 30, contig_names=names, fastq_mutator=mutate, n_barcodes=120, ppb=60, mol_len=9000, mols=1)
+    run_ref(d, ["-k", "30", "-j", "0.5", "-c", "3", "-m", "20-10000", "-e", "3000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
+    run_ref(d, ["-k", "30", "-j", "0.2", "-c", "2", "-m", "1-1000", "-e", "0", "-z", "3000", "-r", "0.2", "-l", "2", "-d", "2", "-t", "1"], "b")
+    # with a multiplicity file that lacks some barcodes (they are rejected as invalid)
+    with open(os.path.join(d, "mult.csv"), "w") as f:
+        bcs = sorted({l.split("\t")[0] for l in open(os.path.join(d, "expected_a_bc.tsv"))})
+        for i, b in enumerate(bcs):
+            if i % 5:
+                f.write("%s,%d\n" % (b, 40 + i))
+    run_ref(d, ["-k", "30", "-j", "0.5", "-c", "2", "-m", "45-200", "-e", "3000", "-z", "500", "-r", "0.05", "-t", "1"], "c",
+            multfile=os.path.join(d, "mult.csv"))
+    # case B: k=60 (two-word keys), longer ends
+    d = make_case("plain_k60", 12, 60, genome_len=120000, mean_contig=15000, n_barcodes=150, ppb=60, mol_len=12000, mols=1)
+    run_ref(d, ["-k", "60", "-j", "0.55", "-c", "5", "-m", "50-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
+    # case C: k=20, low Jaccard threshold, long-read style pseudo pairs (250 bp)
+    d = make_case("long_k20", 13, 20, genome_len=100000, mean_contig=20000, n_barcodes=300, ppb=12, read_len=250, jitter=0, mol_len=15000, mols=1)
+    run_ref(d, ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
+    print("fixtures written under", OUT)
+    subprocess.call(["du", "-sh", OUT])
+
+
+if __name__ == "__main__":
+    main()
