@@ -490,28 +490,11 @@ def main():
 
 
 def nccl_merge_pmap(torch, dist, dev, pa, pb, pc, n_contigs):
-    """The one exchange step: all-gather the ranks' sorted pair keys, form the
-    identical sorted union everywhere, all-reduce the dense 4 x n_keys counter vector."""
-    import numpy as np
-    world = dist.get_world_size()
-    keys = torch.from_numpy((pa.astype(np.int64) << 32) | pb.astype(np.int64)).to(dev)
-    counts = torch.from_numpy(pc.astype(np.int64)).to(dev).reshape(-1, 4)
-    n = torch.tensor([keys.numel()], device=dev, dtype=torch.int64)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    mx = int(max(s.item() for s in sizes))
-    pad = torch.full((mx,), -1, device=dev, dtype=torch.int64)
-    pad[:keys.numel()] = keys
-    gathered = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(gathered, pad)
-    union = torch.unique(torch.cat(gathered))
-    union = union[union >= 0]
-    dense = torch.zeros((union.numel(), 4), device=dev, dtype=torch.int64)
-    if keys.numel():
-        dense[torch.searchsorted(union, keys)] = counts
-    dist.all_reduce(dense, op=dist.ReduceOp.SUM)
+    """the single NCCL exchange: see arcs_b200/merge.py"""
+    from arcs_b200.merge import merge_pmap
+    a, b, c = merge_pmap(pa, pb, pc, dev)
     torch.cuda.synchronize()
-    return int(union.numel())
+    return int(len(a))
 
 
 if __name__ == "__main__":
