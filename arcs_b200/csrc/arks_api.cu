@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <parallel/algorithm>
 #include <string>
 #include <vector>
 
@@ -1095,20 +1096,25 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 			cleanup();
 			return fail(h, ARKS_E_CUDA, "pmap export copy failed");
 		}
-		std::vector<uint64_t> order(n_pairs);
-		std::iota(order.begin(), order.end(), 0);
-		std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {
-			uint64_t kx = ((uint64_t)lexrank[a[x]] << 32) | lexrank[b[x]];
-			uint64_t ky = ((uint64_t)lexrank[a[y]] << 32) | lexrank[b[y]];
-			return kx < ky;
-		});
+		// order by (rank a, rank b): multi-threaded host sort of (key, row) records
+		struct KeyRow
+		{
+			uint64_t key;
+			uint64_t row;
+		};
+		std::vector<KeyRow> order(n_pairs);
+#pragma omp parallel for schedule(static)
+		for (long long i = 0; i < (long long)n_pairs; ++i)
+			order[i] = KeyRow{((uint64_t)lexrank[a[i]] << 32) | lexrank[b[i]], (uint64_t)i};
+		__gnu_parallel::sort(order.begin(), order.end(), [](const KeyRow& x, const KeyRow& y) { return x.key < y.key; });
 		h->pm_a.resize(n_pairs);
 		h->pm_b.resize(n_pairs);
 		h->pm_counts.resize(4 * n_pairs);
-		for (uint64_t i = 0; i < n_pairs; ++i) {
-			h->pm_a[i] = a[order[i]];
-			h->pm_b[i] = b[order[i]];
-			memcpy(&h->pm_counts[4 * i], &c[4 * order[i]], 16);
+#pragma omp parallel for schedule(static)
+		for (long long i = 0; i < (long long)n_pairs; ++i) {
+			h->pm_a[i] = a[order[i].row];
+			h->pm_b[i] = b[order[i].row];
+			memcpy(&h->pm_counts[4 * i], &c[4 * order[i].row], 16);
 		}
 	}
 	cleanup();
