@@ -69,7 +69,7 @@ struct arks_handle
 	uint32_t* d_remap = nullptr;
 	uint32_t n_remap = 0;
 	int map_grid = 0, group_grid = 0, slow_grid = 0;
-	DevBuf worklist, mate_state; // scratch of one map launch (launches on a handle are stream-ordered)
+	DevBuf work; // WorkRecords of one map launch (launches on a handle are stream-ordered)
 	uint32_t* d_work_count = nullptr;
 	int map_mode_pair = 0;
 	// imap
@@ -334,10 +334,9 @@ int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const
 			map_pairs_kernel<2><<<grid, kMapThreads, 0, h->stream>>>(P);
 	} else {
 		int rcw;
-		if ((rcw = ensure(h, h->worklist, n_pairs * 4ull)) || (rcw = ensure(h, h->mate_state, n_pairs * 8ull)))
+		if ((rcw = ensure(h, h->work, n_pairs * sizeof(WorkRecord))))
 			return rcw;
-		P.worklist = (uint32_t*)h->worklist.p;
-		P.mate_state = (uint32_t*)h->mate_state.p;
+		P.work = (WorkRecord*)h->work.p;
 		P.work_count = h->d_work_count;
 		CU(cudaMemsetAsync(h->d_work_count, 0, 4, h->stream));
 		const uint64_t groups = ((uint64_t)n_pairs + kGroupPairs - 1) / kGroupPairs;
@@ -580,7 +579,7 @@ void arks_destroy(arks_handle* h)
 	}
 	for (void* p : {(void*)h->table, (void*)h->d_ictr, (void*)h->d_mctr, (void*)h->d_remap, (void*)h->imap, (void*)h->d_imap_count,
 	         (void*)h->pmap, (void*)h->d_pmap_count, (void*)h->d_scratch, (void*)h->d_jmin, (void*)h->d_nmax, (void*)h->d_work_count,
-	         h->worklist.p, h->mate_state.p})
+	         h->work.p})
 		if (p)
 			cudaFree(p);
 	if (h->own_stream)
@@ -634,7 +633,7 @@ int arks_host_free(void* p)
 // debugging aid (not in the public header): copies internal scratch to the host
 int arks_debug_copy(arks_handle* h, int what, void* dst, size_t bytes)
 {
-	const void* src = what == 0 ? (const void*)h->d_work_count : what == 1 ? h->worklist.p : h->mate_state.p;
+	const void* src = what == 0 ? (const void*)h->d_work_count : h->work.p;
 	CU(cudaStreamSynchronize(h->stream));
 	CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
 	return ARKS_OK;

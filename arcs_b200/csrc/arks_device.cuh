@@ -172,7 +172,7 @@ __device__ __forceinline__ void key_set_byte(Key128& r, int o, uint32_t byte)
 // (Common/ReadsProcessor.cpp:503-534): bytes [0,h) forward, byte h left at 0, later full
 // bytes packed from a cursor that advances 3 bases per byte, hanging byte = one base in
 // bits 7-6.  f = forward packing.  Rare path.
-__device__ __noinline__ Key128 palindrome_key(const Key128& f, int k)
+__device__ __noinline__ Key128 palindrome_key(Key128 f, int k)
 {
 	const int nb = (k + 3) >> 2;
 	const int h = (k >> 3) + ((k & 7) != 0);

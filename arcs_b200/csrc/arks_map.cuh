@@ -27,14 +27,16 @@ constexpr int kMapThreads = kMapWarps * 32;
 constexpr int kRegionBases = 512;               // bases packed per region (32 lanes x 16)
 constexpr int kRegionWords = kRegionBases / 16 + 6;
 constexpr int kRegionInvWords = kRegionBases / 32 + 3;
+constexpr int kMaskWords = kRegionBases / 32 + 2;          // words of TINS / TUNIQ a region can span
+constexpr int kMWords = kRegionInvWords + 2 * kMaskWords;  // per-warp scratch: mismatch mask + the two window masks
 #ifndef ARKS_PROBE_BATCH
-#define ARKS_PROBE_BATCH 2
+#define ARKS_PROBE_BATCH 1
 #endif
 #ifndef ARKS_MAP_MIN_BLOCKS
-#define ARKS_MAP_MIN_BLOCKS 4
+#define ARKS_MAP_MIN_BLOCKS 5
 #endif
 #ifndef ARKS_SEEDS
-#define ARKS_SEEDS 4
+#define ARKS_SEEDS 2
 #endif
 constexpr int kProbeBatch = ARKS_PROBE_BATCH;                  // windows per lane in flight
 constexpr int kSeeds = ARKS_SEEDS;                       // seed windows probed per mate
@@ -87,10 +89,22 @@ struct MapParams
 	//   nmax[len]   = largest number of Ns with !((double)n / (double)len > 0.02)
 	const uint32_t* jmin;
 	const uint32_t* nmax;
-	// pairs the group kernel could not finish: indices + per-mate state (see kMate*)
-	uint32_t* worklist;
+	// pairs the group kernel could not finish: one 64-byte WorkRecord each
+	struct WorkRecord* work;
 	uint32_t* work_count;
-	uint32_t* mate_state; // 2 per pair
+};
+
+// Everything map_slow_kernel needs to start on a deferred pair, in one aligned 64-byte record (so the
+// record of the pair after next can be prefetched by address alone, and the next pair's record is
+// an L1 hit from which ITS bases / contig text / masks are prefetched while the current pair runs).
+struct __align__(16) WorkRecord
+{
+	uint32_t pair;
+	uint32_t off[3];    // read_off[2*pair .. 2*pair+2]
+	uint32_t state[2];  // per mate: kMateSlow / kMateUnknown / the contig end already decided
+	uint32_t meta[2];   // per mate: bit 0 seed hit, bit 1 seed's canonical key is the read's forward strand, bits 8.. seed window
+	uint32_t seed_lo[2], seed_hi[2]; // posinfo of the seed's slot
+	uint32_t pad[4];
 };
 
 // mate_state values: a contig end (or 0) decided by the group kernel, or one of
@@ -256,10 +270,10 @@ __device__ __forceinline__ void track_add(Track& t, uint32_t lane, uint32_t c, u
 // for the windows that could not be resolved by extension).  `list` == nullptr means the
 // windows are 0..n-1 themselves.  Does NOT count kv/ki (the caller classified the windows).
 // ---------------------------------------------------------------------------------------
-#ifdef ARKS_PROBE_INLINE
-#define ARKS_PROBE_ATTR __forceinline__
-#else
+#ifdef ARKS_PROBE_NOINLINE
 #define ARKS_PROBE_ATTR __noinline__
+#else
+#define ARKS_PROBE_ATTR __forceinline__
 #endif
 template <int KW>
 __device__ ARKS_PROBE_ATTR void
@@ -358,9 +372,16 @@ warp_count_windows(const WarpRegion& R, uint32_t nw, uint32_t k, uint32_t lane, 
 }
 
 // bestContig's window loop for a read longer than one region: repack chunk by chunk (cold path)
+// (cold path, not inlined: it gets COPIES of the parameter block, the vote table and the counters so
+// that the hot path's objects never have their address taken and stay in registers / the constant bank)
+struct LongResult
+{
+	Track tr;
+	LaneStats st;
+};
 template <int KW>
-__device__ __noinline__ void
-warp_windows_long(WarpRegion& R, uint16_t* list, const char* src, uint32_t total, const MapParams& P, uint32_t lane, Track& tr, LaneStats& st)
+__device__ __noinline__ LongResult
+warp_windows_long(WarpRegion& R, uint16_t* list, const char* src, uint32_t total, MapParams P, uint32_t lane, Track tr, LaneStats st)
 {
 	const uint32_t cw = kRegionBases - P.k + 1;
 	for (uint32_t c0 = 0; c0 < total; c0 += cw) {
@@ -372,6 +393,7 @@ warp_windows_long(WarpRegion& R, uint16_t* list, const char* src, uint32_t total
 		warp_count_windows(R, nwc, P.k, lane, list, n_list, st);
 		warp_probe_windows<KW>(R, Lc, list, n_list, P, lane, tr, st);
 	}
+	return LongResult{tr, st};
 }
 
 // 16 mismatch bits (LSB-first by base) between a packed stream word and the contig text at
@@ -477,9 +499,23 @@ warp_resolve_read(const WarpRegion& R, uint32_t* M, uint16_t* list, uint32_t L, 
 		const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, m16, 1);
 		if ((lane & 1) == 0)
 			M[lane >> 1] = m16 | (up << 16);
+		// the inserted / unique window masks along the diagonal, loaded once (one word per lane) so that
+		// the window loop below touches shared memory only; words outside the text read as 0 = unresolved
+		{
+			const int64_t wfirst = gw0 >> 5; // arithmetic shift: may be negative
+			const int64_t wi = wfirst + (int64_t)lane;
+			const bool in = lane < (uint32_t)kMaskWords && wi >= 0 && wi < (int64_t)((P.ct_n_bases + 31) >> 5);
+			if (lane < (uint32_t)kMaskWords) {
+				M[kRegionInvWords + lane] = in ? __ldg(P.ct_TINS + wi) : 0u;
+				M[kRegionInvWords + kMaskWords + lane] = in ? __ldg(P.ct_TUNIQ + wi) : 0u;
+			}
+		}
 		__syncwarp();
 	}
 	uint32_t ext_uniq = 0;
+	const uint32_t* TI = M + kRegionInvWords;
+	const uint32_t* TU = TI + kMaskWords;
+	const int64_t gw_first_word = E.have ? ((E.D + (int64_t)(E.same ? 0u : E.off)) >> 5) : 0;
 	for (uint32_t pb = 0; pb < total; pb += 32) {
 		const uint32_t p = pb + lane;
 		bool need = false;
@@ -494,11 +530,11 @@ warp_resolve_read(const WarpRegion& R, uint32_t* M, uint16_t* list, uint32_t L, 
 					if (!window_invalid(M, q, P.k)) {
 						const int64_t gw = E.D + q;
 						if (gw >= E.lo && gw + (int64_t)P.k <= E.hi) {
-							const uint32_t ins = __ldg(P.ct_TINS + (gw >> 5)) >> (gw & 31);
-							if (ins & 1u) {
+							const uint32_t wi = (uint32_t)((gw >> 5) - gw_first_word), bit = (uint32_t)gw & 31u;
+							if ((TI[wi] >> bit) & 1u) {
 								need = false;
 								st.found++;
-								if ((__ldg(P.ct_TUNIQ + (gw >> 5)) >> (gw & 31)) & 1u) {
+								if ((TU[wi] >> bit) & 1u) {
 									st.rec++;
 									ext_uniq++;
 								} else {
@@ -551,18 +587,61 @@ warp_decide(const Track& tr, uint32_t total, const MapParams& P, uint32_t lane, 
 	return (ok && best_cnt) ? best_c : 0u;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// Issues L1 prefetches for everything the general path will touch for this work item: the ASCII
+// bases of the pair, and per unfinished mate with a seed the contig text, the two window masks and
+// the contig-end metadata along the seed's diagonal.  One line per lane.
+__device__ __forceinline__ void prefetch_item(const WorkRecord& rec, const MapParams& P, uint32_t lane)
+{
+	const uint32_t o0 = rec.off[0], o2 = rec.off[2];
+	if (lane < 6) {
+		const char* p = P.bases + o0 + 128u * lane;
+		if (p < P.bases + o2 + 127)
+			prefetch_l1(p);
+		return;
+	}
+	const uint32_t rd = (lane - 6) / 8, what = (lane - 6) % 8;
+	if (rd > 1 || rec.state[rd] != kMateSlow || !(rec.meta[rd] & 1u))
+		return;
+	const uint64_t pi = ((uint64_t)rec.seed_hi[rd] << 32) | rec.seed_lo[rd];
+	const uint64_t g = pi & kPosMask;
+	const uint32_t eidx = (uint32_t)(pi >> 40);
+	// the diagonal starts within one read length of g on either side: cover [g - 256, g + 256)
+	const uint64_t g_lo = g > 256 ? g - 256 : 0;
+	switch (what) {
+	case 0: prefetch_l1(P.ct_T + (g_lo >> 4)); break;
+	case 1: prefetch_l1(P.ct_T + (g_lo >> 4) + 32); break;
+	case 2: prefetch_l1(P.ct_TINS + (g_lo >> 5)); break;
+	case 3: prefetch_l1(P.ct_TINS + (g_lo >> 5) + 16 < P.ct_TINS + (P.ct_n_bases >> 5) ? P.ct_TINS + (g_lo >> 5) + 16 : P.ct_TINS); break;
+	case 4: prefetch_l1(P.ct_TUNIQ + (g_lo >> 5)); break;
+	case 5: prefetch_l1(P.ct_end_g0 + eidx); break;
+	case 6: prefetch_l1(P.ct_end_len + eidx); break;
+	default: prefetch_l1(P.ct_end_cr + eidx); break;
+	}
+}
+
 // One read pair handled by the whole warp (any read length).  Generic path.
 // state0/state1: kMateUnknown for a pair nobody has looked at (validity is checked here), else
 // per mate either kMateSlow (resolve it here) or the contig end already decided elsewhere
 // (then that mate is not touched and none of its counters are bumped).
+#ifdef ARKS_PAIR_NOINLINE
+#define ARKS_PAIR_ATTR __noinline__
+#else
+#define ARKS_PAIR_ATTR __forceinline__
+#endif
 template <int KW>
-__device__ __noinline__ uint32_t
-warp_process_pair(uint32_t pair, uint32_t state0, uint32_t state1, const MapParams& P, WarpRegion* R, uint32_t* M, uint16_t* list,
-    uint32_t lane, LaneStats& st, PairCounters& pc)
+__device__ ARKS_PAIR_ATTR uint32_t
+warp_process_pair(const WorkRecord& rec, const MapParams& P, WarpRegion* R, uint32_t* M, uint16_t* list, uint32_t lane, LaneStats& st,
+    PairCounters& pc)
 {
+	const uint32_t pair = rec.pair, state0 = rec.state[0], state1 = rec.state[1];
 	const bool fresh = state0 == kMateUnknown;
 	const bool todo0 = fresh || state0 == kMateSlow, todo1 = fresh || state1 == kMateSlow;
-	const uint32_t o0 = P.read_off[2 * pair], o1 = P.read_off[2 * pair + 1], o2 = P.read_off[2 * pair + 2];
+	const uint32_t o0 = rec.off[0], o1 = rec.off[1], o2 = rec.off[2];
 	const uint32_t l1 = o1 - o0, l2 = o2 - o1;
 	const bool shortpair = l1 <= (uint32_t)kRegionBases && l2 <= (uint32_t)kRegionBases;
 	uint32_t nn1, no1, nn2, no2;
@@ -582,10 +661,10 @@ warp_process_pair(uint32_t pair, uint32_t state0, uint32_t state1, const MapPara
 		uint64_t seed_pos = 0;
 		uint32_t seed_p = 0;
 		bool seed_found = false, seed_fc = false;
-		if (shortpair && P.use_extension) {
+		if (fresh && shortpair && P.use_extension) {
 			const uint32_t rd = lane / kSeeds, sidx = lane % kSeeds;
 			const uint32_t len = rd ? l2 : l1;
-			if (lane < 2 * kSeeds && len >= P.k && (rd ? todo1 : todo0)) {
+			if (lane < 2 * kSeeds && len >= P.k) {
 				const uint32_t total = len - P.k + 1;
 				seed_p = kSeeds > 1 ? (uint32_t)(((uint64_t)(total - 1) * sidx) / (kSeeds - 1)) : 0;
 				const WarpRegion& Rr = R[rd];
@@ -620,13 +699,24 @@ warp_process_pair(uint32_t pair, uint32_t state0, uint32_t state1, const MapPara
 			if (total) {
 				if (shortpair) {
 					Extension E{};
-					const uint32_t mine = (seed_votes >> (rd * kSeeds)) & ((1u << kSeeds) - 1u);
-					E.have = mine != 0;
+					uint64_t pi;
+					uint32_t sp;
+					bool r_fc;
+					if (fresh) {
+						const uint32_t mine = (seed_votes >> (rd * kSeeds)) & ((1u << kSeeds) - 1u);
+						E.have = mine != 0;
+						const int src = E.have ? rd * kSeeds + __ffs(mine) - 1 : 0;
+						pi = __shfl_sync(0xFFFFFFFFu, seed_pos, src);
+						sp = __shfl_sync(0xFFFFFFFFu, seed_p, src);
+						r_fc = __shfl_sync(0xFFFFFFFFu, (int)seed_fc, src);
+					} else { // the group kernel already probed this mate's seeds
+						const uint32_t meta = rec.meta[rd];
+						E.have = (meta & 1u) != 0;
+						pi = ((uint64_t)rec.seed_hi[rd] << 32) | rec.seed_lo[rd];
+						sp = meta >> 8;
+						r_fc = (meta & 2u) != 0;
+					}
 					if (E.have) {
-						const int src = rd * kSeeds + __ffs(mine) - 1;
-						const uint64_t pi = __shfl_sync(0xFFFFFFFFu, seed_pos, src);
-						const uint32_t sp = __shfl_sync(0xFFFFFFFFu, seed_p, src);
-						const bool r_fc = __shfl_sync(0xFFFFFFFFu, (int)seed_fc, src);
 						const bool c_fc = (pi >> kPosBits) & 1ull;
 						const uint64_t g = pi & kPosMask;
 						const uint32_t eidx = (uint32_t)(pi >> 40);
@@ -640,7 +730,9 @@ warp_process_pair(uint32_t pair, uint32_t state0, uint32_t state1, const MapPara
 					const bool clean = (rd ? (nn2 | no2) : (nn1 | no1)) == 0;
 					warp_resolve_read<KW>(R[rd], M, list, len, total, clean, E, P, lane, tr, st);
 				} else {
-					warp_windows_long<KW>(R[0], list, P.bases + (rd ? o1 : o0), total, P, lane, tr, st);
+					const LongResult lr = warp_windows_long<KW>(R[0], list, P.bases + (rd ? o1 : o0), total, P, lane, tr, st);
+					tr = lr.tr;
+					st = lr.st;
 				}
 			}
 			bool passed;
@@ -703,7 +795,7 @@ template <int KW>
 __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(MapParams P)
 {
 	__shared__ WarpRegion regions[kMapWarps][2];
-	__shared__ uint32_t Ms[kMapWarps][kRegionInvWords];
+	__shared__ uint32_t Ms[kMapWarps][kMWords];
 	__shared__ uint16_t lists[kMapWarps][kRegionBases];
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
@@ -711,8 +803,15 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(M
 	PairCounters pc{0, 0, 0, 0, 0, false};
 	const uint32_t nwarps = gridDim.x * kMapWarps;
 #pragma unroll 1
-	for (uint32_t pair = blockIdx.x * kMapWarps + warp; pair < P.n_pairs; pair += nwarps)
-		warp_process_pair<KW>(pair, kMateUnknown, kMateUnknown, P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
+	for (uint32_t pair = blockIdx.x * kMapWarps + warp; pair < P.n_pairs; pair += nwarps) {
+		WorkRecord rec{};
+		rec.pair = pair;
+		rec.off[0] = P.read_off[2 * pair];
+		rec.off[1] = P.read_off[2 * pair + 1];
+		rec.off[2] = P.read_off[2 * pair + 2];
+		rec.state[0] = rec.state[1] = kMateUnknown;
+		warp_process_pair<KW>(rec, P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
+	}
 	const bool l0 = lane == 0; // pair counters are warp-uniform: count them once
 	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,
 	    pc.overflow);
@@ -953,10 +1052,20 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 			if (lane == 0)
 				base = atomicAdd(P.work_count, (uint32_t)__popc(defer_mask));
 			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			// the record is written by the pair's even lane; it needs the odd lane's read too
+			const uint32_t my_meta = (have_seed ? 1u : 0u) | (seed_fc ? 2u : 0u) | (seed_p << 8);
+			const uint32_t m_meta = __shfl_xor_sync(0xFFFFFFFFu, my_meta, 1);
+			const uint32_t m_lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)seed_pi, 1);
+			const uint32_t m_hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(seed_pi >> 32), 1);
+			const uint32_t m_off = __shfl_xor_sync(0xFFFFFFFFu, off, 1);
+			const uint32_t m_len = __shfl_xor_sync(0xFFFFFFFFu, len, 1);
 			if (defer) {
-				P.worklist[base + __popc(defer_mask & ((1u << lane) - 1u))] = my_pair;
-				P.mate_state[2 * my_pair] = pair_long ? kMateUnknown : (need_slow ? kMateSlow : c_read);
-				P.mate_state[2 * my_pair + 1] = pair_long ? kMateUnknown : (mate_slow ? kMateSlow : c_mate);
+				uint4* dst = reinterpret_cast<uint4*>(P.work + base + __popc(defer_mask & ((1u << lane) - 1u)));
+				const uint32_t s0 = pair_long ? kMateUnknown : (need_slow ? kMateSlow : c_read);
+				const uint32_t s1 = pair_long ? kMateUnknown : (mate_slow ? kMateSlow : c_mate);
+				dst[0] = make_uint4(my_pair, off, m_off, m_off + m_len);
+				dst[1] = make_uint4(s0, s1, my_meta, m_meta);
+				dst[2] = make_uint4((uint32_t)seed_pi, m_lo, (uint32_t)(seed_pi >> 32), m_hi);
 			}
 		}
 		if (exists && even && !defer) {
@@ -984,7 +1093,7 @@ template <int KW>
 __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_slow_kernel(MapParams P)
 {
 	__shared__ WarpRegion regions[kMapWarps][2];
-	__shared__ uint32_t Ms[kMapWarps][kRegionInvWords];
+	__shared__ uint32_t Ms[kMapWarps][kMWords];
 	__shared__ uint16_t lists[kMapWarps][kRegionBases];
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
@@ -992,10 +1101,21 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_slow_kernel(Ma
 	PairCounters pc{0, 0, 0, 0, 0, false};
 	const uint32_t n_work = *P.work_count;
 	const uint32_t nwarps = gridDim.x * kMapWarps;
+	__shared__ WorkRecord recs[kMapWarps];
 #pragma unroll 1
 	for (uint32_t i = blockIdx.x * kMapWarps + warp; i < n_work; i += nwarps) {
-		const uint32_t pair = P.worklist[i];
-		warp_process_pair<KW>(pair, P.mate_state[2 * pair], P.mate_state[2 * pair + 1], P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
+		// software pipeline over work items: the record two items ahead is prefetched by address; the
+		// next item's record (an L1 hit by now) tells which lines ITS mates, contig text and masks live
+		// in, and those are prefetched while the current item is processed.
+		if (i + 2 * nwarps < n_work && lane == 0)
+			prefetch_l1(P.work + i + 2 * nwarps);
+		if (i + nwarps < n_work)
+			prefetch_item(P.work[i + nwarps], P, lane);
+		__syncwarp();
+		if (lane < 4)
+			reinterpret_cast<uint4*>(&recs[warp])[lane] = reinterpret_cast<const uint4*>(P.work + i)[lane];
+		__syncwarp();
+		warp_process_pair<KW>(recs[warp], P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
 	}
 	const bool l0 = lane == 0;
 	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,
