@@ -215,3 +215,113 @@ def test_arks_long_demo_golden_gpu():
                             k=20, j=0.05, c=3, m=(8, 10000), e=30000, z=500, r=0.05, l=0,
                             multfile=os.path.join(d, "barcodeMultiplicityArcs.tsv"))
     assert gv == open(os.path.join(d, "expected_original.gv")).read()
+
+
+def test_device_pointer_entry_points_match_host_ones():
+    """arks_index_add_device / arks_map_pairs_device (what bench.py's device-resident leg calls)"""
+    import torch
+    A = _arks()
+    k, j = 40, 0.5
+    rng = np.random.default_rng(21)
+    genome, contigs = synth.make_draft(rng, 150000, 9000, k)
+    bases, end_off, conreci, _ = synth.contig_end_arrays(genome, contigs, k, end_length=4000)
+    rb, roff, bc = synth.make_reads(rng, genome, n_barcodes=30, pairs_per_barcode=40, mol_len=20000, mols_per_barcode=2, len_jitter=20)
+    host = A.ArksIndex(k, int(end_off[-1]))
+    host.add_ends(bases, end_off, conreci)
+    hst = host.finalize().as_dict()
+    want = host.map_pairs(rb, roff, bc, j)
+    dev = A.ArksIndex(k, int(end_off[-1]))
+    stream = torch.cuda.current_stream()
+    dev.set_stream(stream.cuda_stream)
+    d_bases = torch.from_numpy(bases.copy()).cuda()
+    d_off = torch.from_numpy(end_off.astype(np.int64)).cuda()
+    d_cr = torch.from_numpy(conreci.astype(np.int32)).cuda()
+    dev.add_ends_device(d_bases.data_ptr(), d_off.data_ptr(), d_cr.data_ptr(), end_off)
+    assert dev.finalize().as_dict() == hst
+    d_rb = torch.from_numpy(rb.copy()).cuda()
+    d_roff = torch.from_numpy(roff.astype(np.int64)).to(torch.int32).cuda()
+    d_bc = torch.from_numpy(bc.astype(np.int32)).cuda()
+    d_out = torch.zeros(len(bc), dtype=torch.int32, device="cuda")
+    dev.map_pairs_device(d_rb.data_ptr(), d_roff.data_ptr(), d_bc.data_ptr(), len(bc), len(rb), j, d_out.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    assert dev.map_stats().as_dict() == host.map_stats().as_dict()
+    hi, di = host.imap(), dev.imap()
+    assert sorted(zip(*[x.tolist() for x in hi])) == sorted(zip(*[x.tolist() for x in di]))
+
+
+def test_empty_and_degenerate_inputs():
+    A = _arks()
+    k = 30
+    idx = A.ArksIndex(k, 1000)
+    # ends: empty, shorter than k, all N
+    seqs = [b"", b"ACGT", b"N" * 100]
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    idx.add_ends(bases, off, np.arange(1, len(seqs) + 1, dtype=np.uint32))
+    st = idx.finalize().as_dict()
+    assert st["recorded"] == 0 and st["kmers_valid"] == 0 and st["kmers_null"] == 3  # 71 NULL windows visited every k
+    keys, vals = idx.dump()
+    assert len(vals) == 0
+    # zero pairs, then pairs of empty / tiny / all-N reads
+    idx.map_pairs(np.zeros(0, np.uint8), np.zeros(1, np.uint32), np.zeros(0, np.uint32), 0.5)
+    reads = [b"", b"", b"ACG", b"ACGTACGT", b"N" * 60, b"A" * 60, b"A" * 60, b"C" * 60]
+    rb = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    roff = np.zeros(len(reads) + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(r) for r in reads])
+    got = idx.map_pairs(rb, roff, np.arange(4, dtype=np.uint32), 0.5)
+    km = O.KMap(k, 16)
+    want, ost = km.map_pairs(rb, roff, 0.5)
+    assert np.array_equal(got, want) and not got.any()
+    assert idx.map_stats().as_dict() == ost.as_dict()
+    a, b, c = idx.pair_links(np.zeros(4, np.int32), 0, 10, 1, 0.05, np.zeros(2, np.uint32))
+    assert len(a) == 0
+
+
+def test_table_capacity_error_is_loud():
+    A = _arks()
+    rng = np.random.default_rng(1)
+    seq = synth.ACGT[rng.integers(0, 4, 20000)]
+    idx = A.ArksIndex(31, 16)  # room for ~1k keys only
+    idx.add_ends(seq, np.array([0, len(seq)], dtype=np.uint64), np.array([1], dtype=np.uint32))
+    with pytest.raises(A.ArksError) as e:
+        idx.finalize()
+    assert e.value.code == -4
+
+
+def test_conreci_remap_and_imap_add():
+    """contigs that share a FASTA name are tallied under the first one; arks_imap_add merges external rows"""
+    A = _arks()
+    k, j = 30, 0.4
+    rng = np.random.default_rng(8)
+    genome, contigs = synth.make_draft(rng, 100000, 10000, k, n_runs=0, palindromes=0, iupac=0)
+    bases, end_off, conreci, names = synth.contig_end_arrays(genome, contigs, k, end_length=4000)
+    names = list(names)
+    names[3] = names[1]  # duplicate name
+    ids, uniq = glue.name_ids(names)
+    remap = np.zeros(2 * len(names) + 1, dtype=np.uint32)
+    first = {n: names.index(n) for n in names}
+    for i, n in enumerate(names):
+        remap[2 * i + 1] = 2 * first[n] + 1
+        remap[2 * i + 2] = 2 * first[n] + 2
+    idx = A.ArksIndex(k, int(end_off[-1]))
+    idx.add_ends(bases, end_off, conreci)
+    idx.finalize()
+    idx.set_conreci_remap(remap)
+    rb, roff, bc = synth.make_reads(rng, genome, n_barcodes=40, pairs_per_barcode=50, mol_len=25000, mols_per_barcode=2)
+    got = idx.map_pairs(rb, roff, bc, j)
+    want_rows = {}
+    for b_, c_ in zip(bc.tolist(), got.tolist()):
+        if c_:
+            r = int(remap[c_])
+            ht = want_rows.setdefault((b_, (r - 1) // 2), [0, 0])
+            ht[0 if r & 1 else 1] += 1
+    gb, gc, gh, gt = idx.imap()
+    assert {(b_, c_): [h, t] for b_, c_, h, t in zip(gb.tolist(), gc.tolist(), gh.tolist(), gt.tolist())} == want_rows
+    assert not any(c_ == 3 for c_ in gc.tolist())  # the duplicate never appears under its own index
+    idx.imap_add([0, 1000], [0, 2], [5, 0], [0, 7])
+    gb, gc, gh, gt = idx.imap()
+    rows = {(b_, c_): [h, t] for b_, c_, h, t in zip(gb.tolist(), gc.tolist(), gh.tolist(), gt.tolist())}
+    assert rows[(1000, 2)] == [0, 7]
+    assert rows[(0, 0)] == [want_rows.get((0, 0), [0, 0])[0] + 5, want_rows.get((0, 0), [0, 0])[1]]
