@@ -57,6 +57,11 @@ struct arks_handle
 	uint64_t g_next = 0;      // next free base coordinate (multiple of 32)
 	uint32_t n_global_ends = 0;
 	int use_extension = 1;
+	// membership prefilter over the table's keys (built by arks_index_finalize)
+	unsigned long long* bloom = nullptr;
+	uint64_t bloom_words = 0;
+	int bloom_bits_per_key = 8;
+	int lane_general = 1;
 	// exact integer thresholds for the Jaccard gate and the N-fraction test
 	uint32_t* d_jmin = nullptr;
 	uint32_t* d_nmax = nullptr;
@@ -326,6 +331,9 @@ int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const
 	P.ct_end_cr = (const uint32_t*)h->ct_end_cr.p;
 	P.ct_n_bases = h->g_next;
 	P.use_extension = h->use_extension && h->ct_T.p != nullptr;
+	P.bloom = h->bloom;
+	P.bloom_words = h->bloom_words;
+	P.lane_general = h->lane_general;
 	if (h->map_mode_pair) {
 		int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_pairs + kMapWarps - 1) / kMapWarps, (uint64_t)h->map_grid));
 		if (h->kw == 1)
@@ -496,6 +504,10 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 	const size_t slot_bytes = kSlotBytes;
 	if (const char* s = getenv("ARKS_NO_EXTEND"))
 		h->use_extension = atoi(s) ? 0 : 1;
+	if (const char* s = getenv("ARKS_BLOOM_BITS"))
+		h->bloom_bits_per_key = std::max(0, std::min(64, atoi(s)));
+	if (const char* s = getenv("ARKS_LANE_GENERAL"))
+		h->lane_general = atoi(s) ? 1 : 0;
 	CUC(cudaMalloc(&h->table, h->nslots * slot_bytes));
 	CUC(cudaMemsetAsync(h->table, 0xFF, h->nslots * slot_bytes, h->stream));
 	CUC(cudaMalloc(&h->d_ictr, sizeof(IndexCounters)));
@@ -579,7 +591,7 @@ void arks_destroy(arks_handle* h)
 	}
 	for (void* p : {(void*)h->table, (void*)h->d_ictr, (void*)h->d_mctr, (void*)h->d_remap, (void*)h->imap, (void*)h->d_imap_count,
 	         (void*)h->pmap, (void*)h->d_pmap_count, (void*)h->d_scratch, (void*)h->d_jmin, (void*)h->d_nmax, (void*)h->d_work_count,
-	         h->work.p})
+	         h->work.p, (void*)h->bloom})
 		if (p)
 			cudaFree(p);
 	if (h->own_stream)
@@ -718,6 +730,18 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 		CU(cudaStreamSynchronize(h->stream));
 		if (c.probe_fail)
 			return fail(h, ARKS_E_CAPACITY, "index table full: more distinct k-mers than max_kmers allows");
+		if (h->bloom_bits_per_key > 0 && c.recorded > 0) {
+			h->bloom_words = std::max<uint64_t>(1024, (c.recorded * (uint64_t)h->bloom_bits_per_key + 63) / 64);
+			CU(cudaMalloc(&h->bloom, h->bloom_words * 8));
+			CU(cudaMemsetAsync(h->bloom, 0, h->bloom_words * 8, h->stream));
+			if (h->kw == 1)
+				bloom_build_kernel<1><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->bloom, h->bloom_words);
+			else
+				bloom_build_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->bloom, h->bloom_words);
+			h->launches++;
+			CU(cudaGetLastError());
+			CU(cudaStreamSynchronize(h->stream));
+		}
 		h->istats.kmers_valid = c.kmers_valid;
 		h->istats.kmers_null = c.kmers_null;
 		h->istats.recorded = c.recorded;

@@ -256,11 +256,57 @@ load_slot(const uint8_t* table, uint64_t slot, uint64_t& hi, uint64_t& lo, uint3
 {
 	const uint8_t* p = table + slot * kSlotBytes;
 	uint64_t a, b, c, d;
-	asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+	asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 	hi = a;
 	lo = b;
 	val = (uint32_t)c;
 	posinfo = d;
+}
+
+// Membership prefilter in front of the table: one 64-bit word per key, two bits in each 32-bit half
+// (register-blocked Bloom filter).  Sized to stay resident in the 126 MB L2 for drafts up to a few
+// hundred Mbp, so that the lookup of a read k-mer that is NOT in the draft (every window that
+// overlaps a sequencing error) costs an L2 hit instead of a DRAM line.  No false negatives, so the
+// table is consulted only on a positive and results do not depend on the filter.
+struct BloomProbe
+{
+	uint64_t word;
+	uint32_t m_lo, m_hi;
+};
+
+__device__ __forceinline__ BloomProbe bloom_probe(uint64_t key_hash_value, uint64_t n_words)
+{
+	const uint64_t h2 = (key_hash_value ^ (key_hash_value >> 32)) * 0x9E3779B97F4A7C15ull;
+	const uint32_t lo32 = (uint32_t)h2;
+	BloomProbe b;
+	b.word = __umul64hi(h2, n_words);
+	b.m_lo = (1u << ((lo32 >> 12) & 31u)) | (1u << ((lo32 >> 17) & 31u));
+	b.m_hi = (1u << ((lo32 >> 22) & 31u)) | (1u << (lo32 >> 27));
+	return b;
+}
+
+// L2 residency policies (createpolicy folds into a constant descriptor)
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+__device__ __forceinline__ bool bloom_maybe(const unsigned long long* bloom, const BloomProbe& b)
+{
+	uint32_t lo, hi;
+	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+	    : "=r"(lo), "=r"(hi)
+	    : "l"(bloom + b.word), "l"(l2_policy_evict_last()));
+	return (lo & b.m_lo) == b.m_lo && (hi & b.m_hi) == b.m_hi;
 }
 
 template <int KW>

@@ -365,6 +365,22 @@ __global__ void uniq_mask_kernel(ContigText ct, const uint8_t* table, uint64_t n
 	}
 }
 
+// membership prefilter over every key of the frozen table (bloom_probe in arks_device.cuh); keys whose
+// value is 0 are included: a lookup that finds them counts as "found" (Arcs.cpp:969-971)
+template <int KW>
+__global__ void bloom_build_kernel(const uint8_t* table, uint64_t nslots, unsigned long long* bloom, uint64_t n_words)
+{
+	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t* p = reinterpret_cast<const uint64_t*>(table + sidx * kSlotBytes);
+		const uint64_t hi = p[0], lo = p[1];
+		if (slot_empty<KW>(hi, lo))
+			continue;
+		const Key128 key{hi, KW == 2 ? lo : 0ull};
+		const BloomProbe b = bloom_probe(key_hash<KW>(key), n_words);
+		atomicOr(bloom + b.word, ((unsigned long long)b.m_hi << 32) | b.m_lo);
+	}
+}
+
 // copies (key, value) of every occupied slot to dense arrays (for tests / dumps)
 template <int KW>
 __global__ void dump_kernel(const uint8_t* table, uint64_t nslots, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* vals,

@@ -92,6 +92,10 @@ struct MapParams
 	// pairs the group kernel could not finish: one 64-byte WorkRecord each
 	struct WorkRecord* work;
 	uint32_t* work_count;
+	// membership prefilter over the table's keys (bloom_probe, arks_device.cuh); may be null
+	const unsigned long long* bloom;
+	uint64_t bloom_words;
+	int lane_general; // 0: the group kernel finishes only reads that equal the contig text (A/B runs)
 };
 
 // Everything map_slow_kernel needs to start on a deferred pair, in one aligned 64-byte record (so the
@@ -822,35 +826,110 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(M
 //   stage 1  all lanes pack the 32 reads to 2 bits (flat over the reads' 16-base words, so no lane
 //            idles), invalid-base masks alongside;
 //   stage 2  ONE LANE PER READ: seed probes (two in flight per lane, 64 per warp), the
-//            comparison with the packed contig text along the seed's diagonal, and the
-//            word-parallel inserted/unique mask test.  A read that equals the contig text -- the
-//            common case -- is finished here, with no lane idle;
+//            comparison of the whole read with the packed contig text along the seed's diagonal
+//            (a mismatch bit per base), and the word-parallel window classification: a window whose
+//            k bases are valid and equal the text is found iff the text window was inserted and
+//            recorded iff its key is unique (two bit masks of the contig text); a window that
+//            overlaps a mismatch, or matches a text window that was not inserted, has to be looked
+//            up.  A read that equals the contig text -- the common case -- is finished here;
+//   stage 2b ALL LANES, FLAT over the windows the 32 reads still have to look up: key, hash, the
+//            L2-resident membership filter, and the table only on a filter positive (these windows
+//            carry a sequencing error: almost none of them is in the draft);
 //   stage 3  one lane per pair: if both mates are finished, the pair rule (Arcs.cpp:1280) and
 //            the barcode tally; otherwise the pair goes to a work list with the state of each
-//            mate, and map_slow_kernel resolves the unfinished mates (mismatches, Ns, no seed
-//            hit, not fully inside a contig end, reads longer than kGroupReadBases) with the
-//            general warp-per-pair path.
+//            mate, and map_slow_kernel resolves the unfinished mates (no seed hit, not inside one
+//            contig end, votes for a second contig end, reads longer than kGroupReadBases) with
+//            the general warp-per-pair path.
 #ifndef ARKS_GROUP_WARPS
 #define ARKS_GROUP_WARPS 8
 #endif
 #ifndef ARKS_GROUP_MIN_BLOCKS
-#define ARKS_GROUP_MIN_BLOCKS 4
+#define ARKS_GROUP_MIN_BLOCKS 3
+#endif
+#ifndef ARKS_GROUP_SEEDS
+#define ARKS_GROUP_SEEDS 4
+#endif
+#ifndef ARKS_GROUP_LIST
+#define ARKS_GROUP_LIST 1024
 #endif
 constexpr int kGroupWarps = ARKS_GROUP_WARPS;
 constexpr int kGroupThreads = kGroupWarps * 32;
 constexpr int kGroupMinBlocks = ARKS_GROUP_MIN_BLOCKS;
+constexpr int kGroupSeeds = ARKS_GROUP_SEEDS;  // seed windows tried per read (two at a time)
+constexpr int kGroupListCap = ARKS_GROUP_LIST; // lookups staged per round of stage 2b
 constexpr int kGroupPairs = 16;
 constexpr int kGroupReadBases = 256;
 constexpr int kGroupWStride = kGroupReadBases / 16 + 5; // 21 words: odd stride, +4 slack for extraction
 constexpr int kGroupIStride = kGroupReadBases / 32 + 3; // 11 words
+constexpr int kGroupMStride = kGroupReadBases / 32 + 1; // 9 words: one mask bit per base/window + a zero pad word
 
 struct GroupSmem
 {
 	uint32_t W[32][kGroupWStride];
 	uint32_t INV[32][kGroupIStride];
+	uint32_t BM[32][kGroupMStride]; // per read: mismatch/invalid base mask, then "window overlaps one" (text orientation)
+	uint32_t PM[32][kGroupMStride]; // per read: invalid base mask, then "window overlaps one", then the lookup mask
 	uint32_t woff[33];
-	uint32_t nbad[32]; // per read: N count | other-invalid count << 16
+	uint32_t nbad[32];  // per read: N count | other-invalid count << 16
+	uint32_t rinfo[32]; // per read: number of windows | same-strand flag << 16
+	uint32_t rcend[32]; // per read: the seed's contig end
+	uint32_t pcnt[32];  // per read: lookups found | lookups recorded << 16
+	uint32_t pflag[32]; // per read: a lookup returned another contig end
+	uint16_t list[kGroupListCap]; // staged lookups: read << 8 | window (text orientation)
 };
+
+// seed windows in the order they are tried: both ends first, then the middle, then the quarters
+__device__ __forceinline__ uint32_t seed_window(uint32_t sidx, uint32_t total)
+{
+	const uint32_t last = total - 1;
+	switch (sidx) {
+	case 0: return 0;
+	case 1: return last;
+	case 2: return last >> 1;
+	case 3: return last >> 2;
+	default: return (3 * last) >> 2;
+	}
+}
+
+// bits [s, s + 32) of a LSB-first mask row restricted to [0, len); s may be negative.  The row has
+// a readable word after the one that holds bit len - 1.
+__device__ __forceinline__ uint32_t mask_bits_at(const uint32_t* row, int s, int len)
+{
+	if (s >= len || s + 32 <= 0)
+		return 0u;
+	const int lo = s > 0 ? s : 0;
+	uint32_t v = __funnelshift_r(row[lo >> 5], row[(lo >> 5) + 1], (uint32_t)lo & 31u);
+	const int nvalid = len - lo;
+	if (nvalid < 32)
+		v &= (1u << nvalid) - 1u;
+	if (s < 0)
+		v <<= (uint32_t)(-s);
+	return v;
+}
+
+// X[u] |= X[u + a] over a row of nmw words (words past the row read as 0); in place, ascending
+__device__ __forceinline__ void or_shifted_row(uint32_t* X, uint32_t nmw, uint32_t a)
+{
+	const uint32_t ws = a >> 5, bs = a & 31u;
+	for (uint32_t i = 0; i < nmw; ++i) {
+		const uint32_t i0 = i + ws;
+		const uint32_t lo = i0 < nmw ? X[i0] : 0u;
+		const uint32_t hi = i0 + 1 < nmw ? X[i0 + 1] : 0u;
+		X[i] |= __funnelshift_r(lo, hi, bs);
+	}
+}
+
+// base mask -> window mask: X[u] = OR of X[u .. u + k - 1]  (log2(k) doubling passes)
+__device__ __forceinline__ void dilate_row(uint32_t* X, uint32_t nmw, uint32_t k)
+{
+	uint32_t span = 1;
+	while (span * 2 <= k) {
+		or_shifted_row(X, nmw, span);
+		span *= 2;
+	}
+	if (k > span)
+		or_shifted_row(X, nmw, k - span);
+}
 
 template <int KW>
 __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_kernel(MapParams P)
@@ -860,7 +939,6 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 	const uint32_t lane = threadIdx.x & 31;
 	LaneStats st{0, 0, 0, 0, 0};
 	uint32_t pass = 0, fail = 0, stored = 0, invalid = 0, nogood = 0;
-	bool overflow = false;
 	const uint32_t n_groups = (P.n_pairs + kGroupPairs - 1) / kGroupPairs;
 	const uint32_t nwarps = gridDim.x * kGroupWarps;
 #pragma unroll 1
@@ -923,13 +1001,16 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 		uint64_t seed_pi = 0;
 		uint32_t seed_p = 0;
 		bool seed_fc = false;
+		// a read whose windows are all classified keeps its tallies here until its lookups are back
+		uint32_t r_ki = 0, r_found = 0, r_rec = 0, n_lookup = 0, r_cend = 0;
+		bool r_same = false, classified = false;
 		if (pair_ok && total) {
 			need_slow = true;
 			if (P.use_extension) {
 				const uint32_t* Wr = G.W[lane];
 				// seeds, two probes in flight
 #pragma unroll 1
-				for (uint32_t s0 = 0; s0 < (uint32_t)kSeeds && !have_seed; s0 += 2) {
+				for (uint32_t s0 = 0; s0 < (uint32_t)kGroupSeeds && !have_seed; s0 += 2) {
 					Key128 key[2];
 					uint64_t hi[2], lo[2], pi[2];
 					uint32_t val[2], sp[2];
@@ -937,8 +1018,8 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 #pragma unroll
 					for (int u = 0; u < 2; ++u) {
 						const uint32_t sidx = s0 + u;
-						sp[u] = kSeeds > 1 ? (uint32_t)(((uint64_t)(total - 1) * sidx) / (kSeeds - 1)) : 0;
-						act[u] = sidx < (uint32_t)kSeeds && (clean || !window_invalid(G.INV[lane], sp[u], P.k));
+						sp[u] = seed_window(sidx, total);
+						act[u] = sidx < (uint32_t)kGroupSeeds && (clean || !window_invalid(G.INV[lane], sp[u], P.k));
 						if (act[u]) {
 							Key128 f = extract_window<KW>(Wr, sp[u], P.mask_hi, P.mask_lo);
 							key[u] = canonical_from_forward<KW>(f, P.k, &fc[u]);
@@ -968,8 +1049,10 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 						}
 					}
 				}
-				if (have_seed && clean) {
-					// diagonal of the seed
+				if (have_seed) {
+					// diagonal of the seed.  "Text orientation": coordinate t of the read is text base gw0 + t
+					// (t = read base t on the same strand, the complement of read base len-1-t otherwise);
+					// window u in text orientation is read window u, resp. total-1-u.
 					const bool c_fc = (seed_pi >> kPosBits) & 1ull;
 					const uint64_t g = seed_pi & kPosMask;
 					const uint32_t eidx = (uint32_t)(seed_pi >> 40);
@@ -981,53 +1064,69 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 					const int64_t e_lo = (int64_t)__ldg(P.ct_end_g0 + eidx);
 					const int64_t e_hi = e_lo + (int64_t)__ldg(P.ct_end_len + eidx);
 					const int64_t gw0 = D + q0;
-					if (gw0 >= e_lo && gw0 + (int64_t)(total - 1) + (int64_t)P.k <= e_hi) {
-						// the read against the contig text, 16 bases at a time
-						uint32_t mm = 0;
+					if (gw0 >= e_lo && gw0 + (int64_t)len <= e_hi) {
+						// the read against the contig text, 16 bases at a time: one mismatch bit per base
+						uint32_t* Bm = G.BM[lane];
+						uint32_t* Pm = G.PM[lane];
+						const uint32_t nmw = (len + 31) >> 5;
+						for (uint32_t i = 0; i <= nmw; ++i)
+							Bm[i] = 0u;
+						uint32_t any_mm = 0;
 #pragma unroll 1
-						for (uint32_t j = 0; j < nw && !mm; ++j) {
+						for (uint32_t j = 0; j < nw; ++j) {
 							const uint32_t sw = same ? Wr[j] : rev2(~Wr[nw - 1 - j]);
 							uint32_t m16 = mismatch16(sw, P.ct_T, D + 16 * (int64_t)j, (int64_t)P.ct_n_bases);
-							const uint32_t b0 = 16 * j;
+							const uint32_t b0 = 16 * j; // keep only stream coordinates in [q0, q0 + len)
 							const uint32_t lo_b = q0 > b0 ? min(q0 - b0, 16u) : 0u;
 							const uint32_t hi_b = q0 + len > b0 ? min(q0 + len - b0, 16u) : 0u;
 							m16 &= (hi_b > lo_b) ? (((1u << hi_b) - 1u) & ~((1u << lo_b) - 1u)) : 0u;
-							mm |= m16;
+							reinterpret_cast<uint16_t*>(Bm)[j] = (uint16_t)m16;
+							any_mm |= m16;
 						}
-						if (!mm) {
-							// found iff inserted, recorded iff unique: word-parallel over the bit masks
+						const bool any_bad = any_mm != 0 || !clean;
+						if (!any_bad || P.lane_general) {
+							if (any_bad) {
+								if (q0) // stream -> text orientation
+									for (uint32_t i = 0; i < nmw; ++i)
+										Bm[i] = __funnelshift_r(Bm[i], Bm[i + 1], q0);
+								if (!clean) {
+									const uint32_t* Ir = G.INV[lane];
+									for (uint32_t i = 0; i < nmw; ++i) {
+										const uint32_t v = same ? mask_bits_at(Ir, (int)(32 * i), (int)len)
+										                        : __brev(mask_bits_at(Ir, (int)len - 32 - (int)(32 * i), (int)len));
+										Pm[i] = v;
+										Bm[i] |= v;
+									}
+									Pm[nmw] = 0u;
+									dilate_row(Pm, nmw, P.k);
+								}
+								dilate_row(Bm, nmw, P.k);
+							}
+							// windows in text orientation, 32 at a time
 							const uint64_t w0 = (uint64_t)gw0 >> 5;
 							const uint32_t sh = (uint32_t)gw0 & 31u;
-							const uint32_t nww = (sh + total + 31) >> 5;
-							uint32_t n_ins = 0, n_uq = 0, n_miss = 0;
+							const uint32_t nww = (total + 31) >> 5;
 #pragma unroll 1
 							for (uint32_t w = 0; w < nww; ++w) {
-								const uint32_t first = w == 0 ? sh : 0u;
-								const uint32_t last = min(32u, sh + total - 32u * w);
-								const uint32_t range = (last >= 32 ? 0xFFFFFFFFu : ((1u << last) - 1u)) & ~((1u << first) - 1u);
-								const uint32_t ins = __ldg(P.ct_TINS + w0 + w) & range;
-								const uint32_t uq = __ldg(P.ct_TUNIQ + w0 + w) & ins;
-								n_ins += __popc(ins);
-								n_uq += __popc(uq);
-								n_miss += __popc(range & ~ins);
+								const uint32_t left = total - 32u * w;
+								const uint32_t range = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+								const uint32_t invw = clean ? 0u : (Pm[w] & range);
+								const uint32_t badw = any_bad ? (Bm[w] & range) : 0u;
+								const uint32_t ins = __funnelshift_r(__ldg(P.ct_TINS + w0 + w), __ldg(P.ct_TINS + w0 + w + 1), sh);
+								const uint32_t uq = __funnelshift_r(__ldg(P.ct_TUNIQ + w0 + w), __ldg(P.ct_TUNIQ + w0 + w + 1), sh);
+								const uint32_t res = range & ~badw & ins; // all k bases equal an inserted text window
+								const uint32_t lookup = range & ~invw & ~res;
+								r_ki += __popc(invw);
+								r_found += __popc(res);
+								r_rec += __popc(res & uq);
+								n_lookup += __popc(lookup);
+								Pm[w] = lookup;
 							}
-							if (n_miss == 0) {
+							if (n_lookup == 0 || P.lane_general) {
+								classified = true;
 								need_slow = false;
-								st.kv += total;
-								st.found += n_ins;
-								st.rec += n_uq;
-								st.dups += n_ins - n_uq;
-								bool passed;
-								if (n_uq == 0)
-									passed = 0.0 > P.j_index;
-								else
-									passed = n_uq >= __ldg(P.jmin + total);
-								if (passed) {
-									pass++;
-									c_read = n_uq ? __ldg(P.ct_end_cr + eidx) : 0u;
-								} else {
-									fail++;
-								}
+								r_same = same;
+								r_cend = __ldg(P.ct_end_cr + eidx);
 							}
 						}
 					}
@@ -1039,6 +1138,104 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 				pass++;
 			else
 				fail++;
+		}
+		// ---- stage 2b: the lookups of all 32 reads, flat over the warp
+		const uint32_t my_lookups = classified ? n_lookup : 0u;
+		if (__ballot_sync(0xFFFFFFFFu, my_lookups != 0)) {
+			uint32_t incl_l = my_lookups;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl_l, o);
+				if (lane >= (uint32_t)o)
+					incl_l += t;
+			}
+			const uint32_t excl_l = incl_l - my_lookups;
+			const uint32_t all_lookups = __shfl_sync(0xFFFFFFFFu, incl_l, 31);
+			G.rinfo[lane] = total | ((uint32_t)r_same << 16);
+			G.rcend[lane] = r_cend;
+			G.pcnt[lane] = 0;
+			G.pflag[lane] = 0;
+#pragma unroll 1
+			for (uint32_t base = 0; base < all_lookups; base += kGroupListCap) {
+				__syncwarp();
+				if (my_lookups && excl_l < base + kGroupListCap && incl_l > base) {
+					const uint32_t* Pm = G.PM[lane];
+					const uint32_t nww = (total + 31) >> 5;
+					uint32_t idx = excl_l;
+					for (uint32_t w = 0; w < nww; ++w) {
+						uint32_t m = Pm[w];
+						while (m) {
+							const uint32_t bit = __ffs(m) - 1;
+							m &= m - 1;
+							if (idx >= base && idx < base + kGroupListCap)
+								G.list[idx - base] = (uint16_t)((lane << 8) | (32u * w + bit));
+							idx++;
+						}
+					}
+				}
+				__syncwarp();
+				const uint32_t n_here = min((uint32_t)kGroupListCap, all_lookups - base);
+#pragma unroll 1
+				for (uint32_t f = lane; f < n_here; f += 32) {
+					const uint32_t e = G.list[f];
+					const uint32_t r = e >> 8, u = e & 255u;
+					const uint32_t info = G.rinfo[r];
+					const uint32_t tot = info & 0xFFFFu;
+					const uint32_t p = (info >> 16) ? u : tot - 1 - u;
+					const Key128 fw = extract_window<KW>(G.W[r], p, P.mask_hi, P.mask_lo);
+					bool fc;
+					const Key128 key = canonical_from_forward<KW>(fw, P.k, &fc);
+					const uint64_t h = key_hash<KW>(key);
+					if (P.bloom && !bloom_maybe(P.bloom, bloom_probe(h, P.bloom_words)))
+						continue;
+					uint64_t slot = hash_to_slot(h, P.nslots);
+					while (true) {
+						uint64_t hi, lo, pi;
+						uint32_t val;
+						load_slot(P.table, slot, hi, lo, val, pi);
+						if (slot_matches<KW>(hi, lo, key)) {
+							atomicAdd(&G.pcnt[r], val ? 0x10001u : 1u);
+							if (val && val != G.rcend[r])
+								G.pflag[r] = 1u;
+							break;
+						}
+						if (slot_empty<KW>(hi, lo))
+							break;
+						slot = slot + 1 == P.nslots ? 0 : slot + 1;
+					}
+				}
+			}
+			__syncwarp();
+			if (my_lookups) {
+				if (G.pflag[lane]) {
+					// votes for a second contig end: the general path takes the read from scratch
+					classified = false;
+					need_slow = true;
+				} else {
+					const uint32_t c = G.pcnt[lane];
+					r_found += c & 0xFFFFu;
+					r_rec += c >> 16;
+				}
+			}
+			__syncwarp();
+		}
+		if (classified) {
+			// bestContig's tail (Arcs.cpp:996-1012): every recorded window voted for the seed's contig end
+			st.kv += total - r_ki;
+			st.ki += r_ki;
+			st.found += r_found;
+			st.rec += r_rec;
+			st.dups += r_found - r_rec;
+			bool passed;
+			if (r_rec == 0)
+				passed = 0.0 > P.j_index;
+			else
+				passed = r_rec >= __ldg(P.jmin + total);
+			if (passed) {
+				pass++;
+				c_read = r_rec ? r_cend : 0u;
+			} else {
+				fail++;
+			}
 		}
 		// ---- stage 3: the pair rule for pairs whose mates are both finished (one lane per pair,
 		// Arcs.cpp:1280); every other valid pair goes to the work list of map_slow_kernel
@@ -1084,8 +1281,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 				P.conreci_out[my_pair] = (int32_t)out;
 		}
 	}
-	(void)overflow;
-	flush_counters(P, lane, st, pass, fail, stored, invalid, nogood, overflow);
+	flush_counters(P, lane, st, pass, fail, stored, invalid, nogood, false);
 }
 
 // ---- the pairs the group kernel deferred: one warp per pair, general path -------------------

@@ -136,6 +136,63 @@ def test_map_pairs_ragged_and_long_reads():
     assert idx.map_stats().as_dict() == st.as_dict()
 
 
+@pytest.mark.parametrize("k,j", [(20, 0.05), (31, 0.2), (60, 0.3)])
+def test_map_pairs_chimeric_noisy_and_boundary_reads(k, j):
+    """reads that leave the lane-per-read path of map_groups_kernel in every way it has: votes for a
+    second contig end (chimeras, contig-boundary reads), more staged lookups per group than one round
+    holds (dense errors in 250-bp reads), N runs at both ends, lower case, both strands"""
+    rng = np.random.default_rng(1000 + k)
+    genome, contigs = synth.make_draft(rng, 150000, 6000, k, n_runs=6, palindromes=3)
+    bases, end_off, conreci, _ = synth.contig_end_arrays(genome, contigs, k, end_length=2500)
+    idx, km = _check_index(k, bases, end_off, conreci)
+    G = len(genome)
+    reads = []
+
+    def piece(L):
+        p = int(rng.integers(0, G - L - 1))
+        r = genome[p:p + L].copy()
+        return synth.revcomp(r) if rng.random() < 0.5 else r
+
+    for i in range(400):
+        kind = i % 8
+        L = int(rng.integers(max(k, 60), 257))
+        if kind == 0:  # chimera of two loci
+            a = int(rng.integers(k // 2, L - k // 2 + 1)) if L > k else L
+            r = np.concatenate([piece(a), piece(L - a)]) if 0 < a < L else piece(L)
+        elif kind == 1:  # dense substitutions: most windows have to be looked up
+            r = piece(L)
+            pos = np.arange(int(rng.integers(0, k)), L, max(2, k // 2 + int(rng.integers(0, k))))
+            r[pos] = synth.ACGT[rng.integers(0, 4, len(pos))]
+        elif kind == 2:  # Ns at the ends and in the middle (at most 2 %)
+            r = piece(L)
+            for q in (0, L - 1, L // 2)[: 1 + int(rng.integers(0, 3))]:
+                r[q] = ord("N") if rng.random() < 0.7 else ord("n")
+        elif kind == 3:  # straddles a contig boundary
+            name, s0, e0 = contigs[int(rng.integers(0, len(contigs) - 1))]
+            p = max(0, min(G - L - 1, e0 - int(rng.integers(1, L))))
+            r = genome[p:p + L].copy()
+        elif kind == 4:  # one error near each end: the first two seeds miss
+            r = piece(L)
+            r[int(rng.integers(0, min(k, L)))] = ord("A")
+            r[L - 1 - int(rng.integers(0, min(k, L)))] = ord("C")
+        elif kind == 5:  # lower case + a single substitution
+            r = piece(L) | 0x20
+            r[int(rng.integers(0, L))] = ord("g")
+        elif kind == 6:  # random sequence: nothing found
+            r = synth.ACGT[rng.integers(0, 4, L)].copy()
+        else:
+            r = piece(L)
+        reads.append(r.astype(np.uint8))
+    rb = np.concatenate(reads)
+    roff = np.zeros(len(reads) + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(r) for r in reads])
+    bc = (np.arange(len(reads) // 2) // 10).astype(np.uint32)
+    got = idx.map_pairs(rb, roff, bc, j)
+    want, st = km.map_pairs(rb, roff, j)
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+    assert idx.map_stats().as_dict() == st.as_dict()
+
+
 def test_pair_links_match_oracle():
     k, j = 30, 0.4
     rng = np.random.default_rng(11)
