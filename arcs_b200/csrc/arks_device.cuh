@@ -271,18 +271,32 @@ load_slot(const uint8_t* table, uint64_t slot, uint64_t& hi, uint64_t& lo, uint3
 struct BloomProbe
 {
 	uint64_t word;
-	uint32_t m_lo, m_hi;
+	uint32_t sel; // four 5-bit bit indices: two in the low half of the word, two in the high half
 };
 
 __device__ __forceinline__ BloomProbe bloom_probe(uint64_t key_hash_value, uint64_t n_words)
 {
 	const uint64_t h2 = (key_hash_value ^ (key_hash_value >> 32)) * 0x9E3779B97F4A7C15ull;
-	const uint32_t lo32 = (uint32_t)h2;
 	BloomProbe b;
 	b.word = __umul64hi(h2, n_words);
-	b.m_lo = (1u << ((lo32 >> 12) & 31u)) | (1u << ((lo32 >> 17) & 31u));
-	b.m_hi = (1u << ((lo32 >> 22) & 31u)) | (1u << (lo32 >> 27));
+	b.sel = (uint32_t)h2 >> 12;
 	return b;
+}
+
+__device__ __forceinline__ uint32_t bloom_mask_lo(uint32_t sel)
+{
+	return (1u << (sel & 31u)) | (1u << ((sel >> 5) & 31u));
+}
+
+__device__ __forceinline__ uint32_t bloom_mask_hi(uint32_t sel)
+{
+	return (1u << ((sel >> 10) & 31u)) | (1u << ((sel >> 15) & 31u));
+}
+
+__device__ __forceinline__ bool bloom_test(uint32_t sel, uint32_t lo, uint32_t hi)
+{
+	const uint32_t m_lo = bloom_mask_lo(sel), m_hi = bloom_mask_hi(sel);
+	return (lo & m_lo) == m_lo && (hi & m_hi) == m_hi;
 }
 
 // L2 residency policies (createpolicy folds into a constant descriptor)
@@ -300,13 +314,18 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
 	return pol;
 }
 
-__device__ __forceinline__ bool bloom_maybe(const unsigned long long* bloom, const BloomProbe& b)
+__device__ __forceinline__ void bloom_load(const unsigned long long* bloom, const BloomProbe& b, uint32_t& lo, uint32_t& hi)
 {
-	uint32_t lo, hi;
 	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
 	    : "=r"(lo), "=r"(hi)
 	    : "l"(bloom + b.word), "l"(l2_policy_evict_last()));
-	return (lo & b.m_lo) == b.m_lo && (hi & b.m_hi) == b.m_hi;
+}
+
+__device__ __forceinline__ bool bloom_maybe(const unsigned long long* bloom, const BloomProbe& b)
+{
+	uint32_t lo, hi;
+	bloom_load(bloom, b, lo, hi);
+	return bloom_test(b.sel, lo, hi);
 }
 
 template <int KW>

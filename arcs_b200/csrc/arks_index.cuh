@@ -377,7 +377,7 @@ __global__ void bloom_build_kernel(const uint8_t* table, uint64_t nslots, unsign
 			continue;
 		const Key128 key{hi, KW == 2 ? lo : 0ull};
 		const BloomProbe b = bloom_probe(key_hash<KW>(key), n_words);
-		atomicOr(bloom + b.word, ((unsigned long long)b.m_hi << 32) | b.m_lo);
+		atomicOr(bloom + b.word, ((unsigned long long)bloom_mask_hi(b.sel) << 32) | bloom_mask_lo(b.sel));
 	}
 }
 

@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(M
 #define ARKS_GROUP_SEEDS 4
 #endif
 #ifndef ARKS_GROUP_LIST
-#define ARKS_GROUP_LIST 1024
+#define ARKS_GROUP_LIST 512
 #endif
 constexpr int kGroupWarps = ARKS_GROUP_WARPS;
 constexpr int kGroupThreads = kGroupWarps * 32;
@@ -871,12 +871,47 @@ struct GroupSmem
 	uint32_t PM[32][kGroupMStride]; // per read: invalid base mask, then "window overlaps one", then the lookup mask
 	uint32_t woff[33];
 	uint32_t nbad[32];  // per read: N count | other-invalid count << 16
-	uint32_t rinfo[32]; // per read: number of windows | same-strand flag << 16
-	uint32_t rcend[32]; // per read: the seed's contig end
-	uint32_t pcnt[32];  // per read: lookups found | lookups recorded << 16
-	uint32_t pflag[32]; // per read: a lookup returned another contig end
-	uint16_t list[kGroupListCap]; // staged lookups: read << 8 | window (text orientation)
+	uint32_t rinfo[32];  // per read: number of windows | same-strand flag << 16
+	uint32_t rcend[32];  // per read: the seed's contig end
+	uint32_t rcend2[32]; // per read: a second contig end its lookups voted for (0: none yet)
+	uint32_t pcnt[32];   // per read: lookups found | lookups recorded << 16
+	uint32_t pcnt2[32];  // per read: lookups recorded for rcend2 | (a third contig end turned up) << 31
+	uint16_t list[kGroupListCap]; // staged lookups: read << 11 | first window (text orientation) << 3 | windows - 1
+	uint16_t pos[256];            // filter positives of one round: read << 8 | read window
+	uint32_t npos;
 };
+
+constexpr uint32_t kChunkWindows = 8; // consecutive windows one lane looks up with a rolling key
+#ifndef ARKS_LOOKUP_BATCH
+#define ARKS_LOOKUP_BATCH 4
+#endif
+constexpr int kLookupBatch = ARKS_LOOKUP_BATCH; // filter loads in flight per lane
+
+// bits b of word w with lo <= 32 w + b < hi
+__device__ __forceinline__ uint32_t word_range_mask(uint32_t lo, uint32_t hi, uint32_t w)
+{
+	const uint32_t w0 = 32u * w;
+	const uint32_t a = lo > w0 ? min(lo - w0, 32u) : 0u;
+	const uint32_t b = hi > w0 ? min(hi - w0, 32u) : 0u;
+	if (b <= a)
+		return 0u;
+	return (b >= 32u ? 0xFFFFFFFFu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+}
+
+// number of chunks of at most kChunkWindows consecutive set bits a mask word splits into
+__device__ __forceinline__ uint32_t count_chunks(uint32_t m)
+{
+	uint32_t n = 0;
+	while (m) {
+		const uint32_t s = __ffs(m) - 1;
+		const uint32_t t = m >> s;
+		const uint32_t run = t == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs(~t) - 1u;
+		const uint32_t c = min(run, kChunkWindows);
+		m &= ~((c >= 32u ? 0xFFFFFFFFu : ((1u << c) - 1u)) << s);
+		n++;
+	}
+	return n;
+}
 
 // seed windows in the order they are tried: both ends first, then the middle, then the quarters
 __device__ __forceinline__ uint32_t seed_window(uint32_t sidx, uint32_t total)
@@ -1064,7 +1099,15 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 					const int64_t e_lo = (int64_t)__ldg(P.ct_end_g0 + eidx);
 					const int64_t e_hi = e_lo + (int64_t)__ldg(P.ct_end_len + eidx);
 					const int64_t gw0 = D + q0;
-					if (gw0 >= e_lo && gw0 + (int64_t)len <= e_hi) {
+					// windows [u_lo, u_hi) lie inside the seed's contig end; the others (a read that runs over
+					// the end of a contig end) are looked up.  Without the second-candidate logic only reads
+					// inside one end are finished here.
+					const bool all_inside = gw0 >= e_lo && gw0 + (int64_t)len <= e_hi;
+					const bool in_text = gw0 >= 0 && gw0 + (int64_t)len <= (int64_t)P.ct_n_bases;
+					if (in_text && (all_inside || P.lane_general)) {
+						const uint32_t u_lo = e_lo > gw0 ? (uint32_t)min((int64_t)total, e_lo - gw0) : 0u;
+						const int64_t hi_s = e_hi - (int64_t)P.k - gw0 + 1;
+						const uint32_t u_hi = hi_s <= 0 ? 0u : (uint32_t)min((int64_t)total, hi_s);
 						// the read against the contig text, 16 bases at a time: one mismatch bit per base
 						uint32_t* Bm = G.BM[lane];
 						uint32_t* Pm = G.PM[lane];
@@ -1114,12 +1157,13 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 								const uint32_t badw = any_bad ? (Bm[w] & range) : 0u;
 								const uint32_t ins = __funnelshift_r(__ldg(P.ct_TINS + w0 + w), __ldg(P.ct_TINS + w0 + w + 1), sh);
 								const uint32_t uq = __funnelshift_r(__ldg(P.ct_TUNIQ + w0 + w), __ldg(P.ct_TUNIQ + w0 + w + 1), sh);
-								const uint32_t res = range & ~badw & ins; // all k bases equal an inserted text window
+								const uint32_t inside = all_inside ? range : word_range_mask(u_lo, u_hi, w);
+								const uint32_t res = inside & ~badw & ins; // all k bases equal an inserted window of this contig end
 								const uint32_t lookup = range & ~invw & ~res;
 								r_ki += __popc(invw);
 								r_found += __popc(res);
 								r_rec += __popc(res & uq);
-								n_lookup += __popc(lookup);
+								n_lookup += count_chunks(lookup);
 								Pm[w] = lookup;
 							}
 							if (n_lookup == 0 || P.lane_general) {
@@ -1139,8 +1183,9 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 			else
 				fail++;
 		}
-		// ---- stage 2b: the lookups of all 32 reads, flat over the warp
-		const uint32_t my_lookups = classified ? n_lookup : 0u;
+		// ---- stage 2b: the lookups of all 32 reads, flat over the warp in chunks of up to kChunkWindows
+		// consecutive windows (rolling key within a chunk)
+		const uint32_t my_lookups = classified ? n_lookup : 0u; // chunks
 		if (__ballot_sync(0xFFFFFFFFu, my_lookups != 0)) {
 			uint32_t incl_l = my_lookups;
 			for (int o = 1; o < 32; o <<= 1) {
@@ -1152,8 +1197,12 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 			const uint32_t all_lookups = __shfl_sync(0xFFFFFFFFu, incl_l, 31);
 			G.rinfo[lane] = total | ((uint32_t)r_same << 16);
 			G.rcend[lane] = r_cend;
+			G.rcend2[lane] = 0;
 			G.pcnt[lane] = 0;
-			G.pflag[lane] = 0;
+			G.pcnt2[lane] = 0;
+			// where base b of a left-aligned forward key sits, for b = k - 1 (the base a roll brings in)
+			const uint32_t kin = P.k - 1;
+			const uint32_t in_shift = 62u - 2u * (kin & 31u);
 #pragma unroll 1
 			for (uint32_t base = 0; base < all_lookups; base += kGroupListCap) {
 				__syncwarp();
@@ -1164,10 +1213,13 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 					for (uint32_t w = 0; w < nww; ++w) {
 						uint32_t m = Pm[w];
 						while (m) {
-							const uint32_t bit = __ffs(m) - 1;
-							m &= m - 1;
+							const uint32_t s = __ffs(m) - 1;
+							const uint32_t t = m >> s;
+							const uint32_t run = t == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs(~t) - 1u;
+							const uint32_t c = min(run, kChunkWindows);
+							m &= ~((c >= 32u ? 0xFFFFFFFFu : ((1u << c) - 1u)) << s);
 							if (idx >= base && idx < base + kGroupListCap)
-								G.list[idx - base] = (uint16_t)((lane << 8) | (32u * w + bit));
+								G.list[idx - base] = (uint16_t)((lane << 11) | ((32u * w + s) << 3) | (c - 1u));
 							idx++;
 						}
 					}
@@ -1175,66 +1227,136 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 				__syncwarp();
 				const uint32_t n_here = min((uint32_t)kGroupListCap, all_lookups - base);
 #pragma unroll 1
-				for (uint32_t f = lane; f < n_here; f += 32) {
-					const uint32_t e = G.list[f];
-					const uint32_t r = e >> 8, u = e & 255u;
-					const uint32_t info = G.rinfo[r];
-					const uint32_t tot = info & 0xFFFFu;
-					const uint32_t p = (info >> 16) ? u : tot - 1 - u;
-					const Key128 fw = extract_window<KW>(G.W[r], p, P.mask_hi, P.mask_lo);
-					bool fc;
-					const Key128 key = canonical_from_forward<KW>(fw, P.k, &fc);
-					const uint64_t h = key_hash<KW>(key);
-					if (P.bloom && !bloom_maybe(P.bloom, bloom_probe(h, P.bloom_words)))
-						continue;
-					uint64_t slot = hash_to_slot(h, P.nslots);
-					while (true) {
-						uint64_t hi, lo, pi;
-						uint32_t val;
-						load_slot(P.table, slot, hi, lo, val, pi);
-						if (slot_matches<KW>(hi, lo, key)) {
-							atomicAdd(&G.pcnt[r], val ? 0x10001u : 1u);
-							if (val && val != G.rcend[r])
-								G.pflag[r] = 1u;
-							break;
+				for (uint32_t f0 = 0; f0 < n_here; f0 += 32) {
+					// 32 chunks at a time through the filter; the positives (rare) are collected and consulted
+					// in the table afterwards, all at once, so that their DRAM round trips overlap
+					if (lane == 0)
+						G.npos = 0;
+					__syncwarp();
+					const uint32_t f = f0 + lane;
+					if (f < n_here) {
+						const uint32_t e = G.list[f];
+						const uint32_t r = e >> 11, u0 = (e >> 3) & 255u, n = (e & 7u) + 1u;
+						const uint32_t info = G.rinfo[r];
+						const uint32_t tot = info & 0xFFFFu;
+						const uint32_t p_lo = (info >> 16) ? u0 : tot - u0 - n; // read windows [p_lo, p_lo + n)
+						const uint32_t* Wr = G.W[r];
+						Key128 fw = extract_window<KW>(Wr, p_lo, P.mask_hi, P.mask_lo);
+						Key128 rc = revcomp_key<KW>(fw, P.k);
+#pragma unroll 1
+						for (uint32_t i0 = 0; i0 < n; i0 += kLookupBatch) {
+							// kLookupBatch filter words in flight
+							uint32_t flo[kLookupBatch], fhi[kLookupBatch], sel[kLookupBatch];
+#pragma unroll
+							for (int jj = 0; jj < kLookupBatch; ++jj) {
+								flo[jj] = fhi[jj] = 0xFFFFFFFFu;
+								sel[jj] = 0u;
+								if (i0 + jj < n) {
+									const bool f_less = (fw.hi < rc.hi) || (fw.hi == rc.hi && fw.lo < rc.lo);
+									const bool equal = (fw.hi == rc.hi) && (fw.lo == rc.lo);
+									const Key128 key = equal ? palindrome_key(fw, (int)P.k) : (f_less ? fw : rc);
+									if (P.bloom) {
+										const BloomProbe bp = bloom_probe(key_hash<KW>(key), P.bloom_words);
+										sel[jj] = bp.sel;
+										bloom_load(P.bloom, bp, flo[jj], fhi[jj]);
+									}
+									// roll to the next window: read base p + k comes in
+									const uint32_t q = p_lo + i0 + jj + P.k;
+									const uint64_t nb = (Wr[q >> 4] >> (30u - 2u * (q & 15u))) & 3u;
+									if (KW == 1) {
+										fw.hi = (fw.hi << 2) | (nb << in_shift);
+										rc.hi = ((rc.hi >> 2) | ((3ull - nb) << 62)) & P.mask_hi;
+									} else {
+										fw.hi = (fw.hi << 2) | (fw.lo >> 62);
+										fw.lo <<= 2;
+										if (kin < 32)
+											fw.hi |= nb << in_shift;
+										else
+											fw.lo |= nb << in_shift;
+										rc.lo = ((rc.lo >> 2) | (rc.hi << 62)) & P.mask_lo;
+										rc.hi = ((rc.hi >> 2) | ((3ull - nb) << 62)) & P.mask_hi;
+									}
+								}
+							}
+#pragma unroll
+							for (int jj = 0; jj < kLookupBatch; ++jj) {
+								if (i0 + jj < n && bloom_test(sel[jj], flo[jj], fhi[jj]))
+									G.pos[atomicAdd(&G.npos, 1u)] = (uint16_t)((r << 8) | (p_lo + i0 + jj));
+							}
 						}
-						if (slot_empty<KW>(hi, lo))
-							break;
-						slot = slot + 1 == P.nslots ? 0 : slot + 1;
 					}
-				}
-			}
-			__syncwarp();
-			if (my_lookups) {
-				if (G.pflag[lane]) {
-					// votes for a second contig end: the general path takes the read from scratch
-					classified = false;
-					need_slow = true;
-				} else {
-					const uint32_t c = G.pcnt[lane];
-					r_found += c & 0xFFFFu;
-					r_rec += c >> 16;
+					__syncwarp();
+					const uint32_t n_pos = G.npos;
+#pragma unroll 1
+					for (uint32_t i = lane; i < n_pos; i += 32) {
+						const uint32_t e = G.pos[i];
+						const uint32_t r = e >> 8;
+						bool fc;
+						const Key128 key = canonical_from_forward<KW>(extract_window<KW>(G.W[r], e & 255u, P.mask_hi, P.mask_lo), P.k, &fc);
+						uint64_t slot = hash_to_slot(key_hash<KW>(key), P.nslots);
+						while (true) {
+							uint64_t hi, lo, pi;
+							uint32_t val;
+							load_slot(P.table, slot, hi, lo, val, pi);
+							if (slot_matches<KW>(hi, lo, key)) {
+								atomicAdd(&G.pcnt[r], val ? 0x10001u : 1u);
+								if (val && val != G.rcend[r]) {
+									// a vote for another contig end: one more candidate is tracked
+									const uint32_t old = atomicCAS(&G.rcend2[r], 0u, val);
+									if (old == 0u || old == val)
+										atomicAdd(&G.pcnt2[r], 1u);
+									else
+										atomicOr(&G.pcnt2[r], 0x80000000u);
+								}
+								break;
+							}
+							if (slot_empty<KW>(hi, lo))
+								break;
+							slot = slot + 1 == P.nslots ? 0 : slot + 1;
+						}
+					}
+					__syncwarp();
 				}
 			}
 			__syncwarp();
 		}
 		if (classified) {
-			// bestContig's tail (Arcs.cpp:996-1012): every recorded window voted for the seed's contig end
-			st.kv += total - r_ki;
-			st.ki += r_ki;
-			st.found += r_found;
-			st.rec += r_rec;
-			st.dups += r_found - r_rec;
-			bool passed;
-			if (r_rec == 0)
-				passed = 0.0 > P.j_index;
-			else
-				passed = r_rec >= __ldg(P.jmin + total);
-			if (passed) {
-				pass++;
-				c_read = r_rec ? r_cend : 0u;
+			// bestContig's tail (Arcs.cpp:996-1012): the recorded windows voted for the seed's contig end,
+			// except the looked-up ones that voted for a second one
+			uint32_t v1 = r_rec, v2 = 0, c2 = 0;
+			bool third = false;
+			if (my_lookups) {
+				const uint32_t c = G.pcnt[lane], d = G.pcnt2[lane];
+				third = (d >> 31) != 0 || (d != 0 && !P.lane_general);
+				v2 = d & 0x7FFFFFFFu;
+				c2 = G.rcend2[lane];
+				r_found += c & 0xFFFFu;
+				r_rec += c >> 16;
+				v1 = r_rec - v2;
+			}
+			if (third) {
+				// votes for three contig ends: the general path takes the read from scratch
+				need_slow = true;
 			} else {
-				fail++;
+				st.kv += total - r_ki;
+				st.ki += r_ki;
+				st.found += r_found;
+				st.rec += r_rec;
+				st.dups += r_found - r_rec;
+				// argmax, ties -> smallest contig end (std::map order + strict '<', Arcs.cpp:998-1003)
+				const uint32_t best = max(v1, v2);
+				const uint32_t best_c = (v2 > v1 || (v2 == v1 && c2 < r_cend)) ? c2 : r_cend;
+				bool passed;
+				if (best == 0)
+					passed = 0.0 > P.j_index;
+				else
+					passed = best >= __ldg(P.jmin + total);
+				if (passed) {
+					pass++;
+					c_read = best ? best_c : 0u;
+				} else {
+					fail++;
+				}
 			}
 		}
 		// ---- stage 3: the pair rule for pairs whose mates are both finished (one lane per pair,
