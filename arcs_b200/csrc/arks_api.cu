@@ -494,7 +494,18 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		CUC(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
 	}
+	// slots per key: load factor 0.5 (one probe per lookup almost always) unless the table would not leave
+	// room for the rest in device memory -- a 3 Gbp draft has 3e9 keys, 96 GB of slots at load 1 -- then as
+	// dense as 0.85 (absent keys rarely reach the table: the membership filter answers first)
 	double load = 0.5;
+	{
+		size_t free_b = 0, total_b = 0;
+		CUC(cudaMemGetInfo(&free_b, &total_b));
+		const double budget = 0.6 * (double)free_b;
+		const double want = (double)max_kmers / load * kSlotBytes;
+		if (want > budget)
+			load = std::min(0.85, (double)max_kmers * kSlotBytes / budget);
+	}
 	if (const char* s = getenv("ARKS_TABLE_LOAD")) {
 		double v = atof(s);
 		if (v > 0.05 && v < 0.95)

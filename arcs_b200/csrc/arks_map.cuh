@@ -165,6 +165,12 @@ imap_add(unsigned long long* imap, uint64_t mask, unsigned long long* count, uin
 	}
 }
 
+__device__ __noinline__ void
+imap_add_call(unsigned long long* imap, uint64_t mask, unsigned long long* count, uint32_t barcode, uint32_t contig, uint32_t head_inc, uint32_t tail_inc)
+{
+	imap_add(imap, mask, count, barcode, contig, head_inc, tail_inc);
+}
+
 // Packs a region of len <= kRegionBases bases.  Returns warp-uniform counts of N/n and of
 // other invalid characters.
 __device__ __forceinline__ void
@@ -883,7 +889,7 @@ struct GroupSmem
 
 constexpr uint32_t kChunkWindows = 8; // consecutive windows one lane looks up with a rolling key
 #ifndef ARKS_LOOKUP_BATCH
-#define ARKS_LOOKUP_BATCH 4
+#define ARKS_LOOKUP_BATCH 1
 #endif
 constexpr int kLookupBatch = ARKS_LOOKUP_BATCH; // filter loads in flight per lane
 
@@ -966,6 +972,57 @@ __device__ __forceinline__ void dilate_row(uint32_t* X, uint32_t nmw, uint32_t k
 		or_shifted_row(X, nmw, k - span);
 }
 
+// The lane-per-read kernel is instruction-cache bound as soon as its hot loop outgrows ~2.5k SASS
+// instructions (profiles/: stall_no_inst 4 % -> 36 % between two builds that differ in code size only),
+// so everything that is needed at several places or only rarely is a real function call:
+
+// canonical key of read window p (forward packing in W) and its slot hash
+struct KeyHash
+{
+	Key128 key;
+	uint64_t hash;
+	uint32_t fwd_is_canonical;
+};
+template <int KW>
+__device__ __forceinline__ KeyHash window_key_hash(const uint32_t* W, uint32_t p, uint32_t k, uint64_t mask_hi, uint64_t mask_lo)
+{
+	KeyHash r;
+	bool fc;
+	const Key128 f = extract_window<KW>(W, p, mask_hi, mask_lo);
+	r.key = canonical_from_forward<KW>(f, k, &fc);
+	r.hash = key_hash<KW>(r.key);
+	r.fwd_is_canonical = fc;
+	return r;
+}
+
+struct ChainResult
+{
+	uint64_t posinfo;
+	uint32_t val;
+	uint32_t found;
+};
+
+// the home slot held another key: walk the probe sequence (rare at load 0.5)
+template <int KW>
+__device__ __noinline__ ChainResult slot_chain_find(const uint8_t* table, uint64_t nslots, uint64_t slot, uint64_t key_hi, uint64_t key_lo)
+{
+	const Key128 key{key_hi, key_lo};
+	ChainResult r;
+	while (true) {
+		slot = slot + 1 == nslots ? 0 : slot + 1;
+		uint64_t hi, lo;
+		load_slot(table, slot, hi, lo, r.val, r.posinfo);
+		r.found = slot_matches<KW>(hi, lo, key);
+		if (r.found || slot_empty<KW>(hi, lo))
+			return r;
+	}
+}
+
+__device__ __noinline__ void dilate_row_call(uint32_t* X, uint32_t nmw, uint32_t k)
+{
+	dilate_row(X, nmw, k);
+}
+
 template <int KW>
 __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_kernel(MapParams P)
 {
@@ -993,6 +1050,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 		const uint32_t nwords = (exists && !pair_long) ? (len + 15) >> 4 : 0;
 		// ---- stage 1: flat packing
 		uint32_t incl = nwords;
+#pragma unroll 1
 		for (int o = 1; o < 32; o <<= 1) {
 			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
 			if (lane >= (uint32_t)o)
@@ -1016,7 +1074,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 			const uint32_t roff = P.read_off[2 * pair0 + r];
 			const uint32_t rlen = P.read_off[2 * pair0 + r + 1] - roff;
 			uint32_t inv16, nn, no;
-			G.W[r][j] = pack_group(P.bases + roff, rlen, j, &inv16, &nn, &no);
+			G.W[r][j] = pack_group_compact(P.bases + roff, rlen, j, &inv16, &nn, &no);
 			reinterpret_cast<uint16_t*>(G.INV[r])[j] = (uint16_t)inv16;
 			if (inv16)
 				atomicAdd(&G.nbad[r], nn | (no << 16));
@@ -1026,7 +1084,8 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 		const uint32_t bad = G.nbad[lane];
 		const uint32_t n_n = bad & 0xFFFFu, n_other = bad >> 16;
 		const bool clean = bad == 0;
-		const bool ok = exists && !pair_long && read_ok(n_n, n_other, len, P.nmax);
+		// checkReadSequence (Arcs.cpp:366-389) through the exact integer table (reads here are <= kGroupReadBases)
+		const bool ok = exists && !pair_long && n_other == 0 && (n_n == 0 || n_n <= __ldg(P.nmax + min(len, (uint32_t)kRegionBases)));
 		const bool mate_ok = __shfl_xor_sync(0xFFFFFFFFu, (int)ok, 1); // (not inside '&&': every lane must shuffle)
 		const bool pair_ok = ok && mate_ok;
 		const uint32_t total = (len >= P.k) ? len - P.k + 1 : 0;
@@ -1046,41 +1105,59 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 				// seeds, two probes in flight
 #pragma unroll 1
 				for (uint32_t s0 = 0; s0 < (uint32_t)kGroupSeeds && !have_seed; s0 += 2) {
-					Key128 key[2];
-					uint64_t hi[2], lo[2], pi[2];
-					uint32_t val[2], sp[2];
-					bool fc[2], act[2];
-#pragma unroll
-					for (int u = 0; u < 2; ++u) {
+					// the two keys come out of ONE copy of the key code (rolled loop, results moved into named
+					// registers); then both probes are issued back to back
+					Key128 key0{0, 0}, key1{0, 0};
+					uint64_t slot0 = 0, slot1 = 0;
+					uint32_t sp0 = 0, sp1 = 0;
+					bool fc0 = false, fc1 = false, act0 = false, act1 = false;
+#pragma unroll 1
+					for (uint32_t u = 0; u < 2; ++u) {
 						const uint32_t sidx = s0 + u;
-						sp[u] = seed_window(sidx, total);
-						act[u] = sidx < (uint32_t)kGroupSeeds && (clean || !window_invalid(G.INV[lane], sp[u], P.k));
-						if (act[u]) {
-							Key128 f = extract_window<KW>(Wr, sp[u], P.mask_hi, P.mask_lo);
-							key[u] = canonical_from_forward<KW>(f, P.k, &fc[u]);
-							load_slot(P.table, hash_to_slot(key_hash<KW>(key[u]), P.nslots), hi[u], lo[u], val[u], pi[u]);
+						const uint32_t sp = seed_window(sidx, total);
+						const bool act = sidx < (uint32_t)kGroupSeeds && (clean || !window_invalid(G.INV[lane], sp, P.k));
+						KeyHash kh{{0, 0}, 0, 0};
+						if (act)
+							kh = window_key_hash<KW>(Wr, sp, P.k, P.mask_hi, P.mask_lo);
+						const uint64_t slot = hash_to_slot(kh.hash, P.nslots);
+						if (u == 0) {
+							key0 = kh.key, slot0 = slot, sp0 = sp, fc0 = kh.fwd_is_canonical != 0, act0 = act;
+						} else {
+							key1 = kh.key, slot1 = slot, sp1 = sp, fc1 = kh.fwd_is_canonical != 0, act1 = act;
 						}
 					}
-#pragma unroll
-					for (int u = 0; u < 2; ++u) {
-						if (act[u] && !have_seed) {
-							bool found = slot_matches<KW>(hi[u], lo[u], key[u]);
-							bool empty = slot_empty<KW>(hi[u], lo[u]);
-							if (!found && !empty) {
-								uint64_t slot = hash_to_slot(key_hash<KW>(key[u]), P.nslots);
-								do {
-									slot = slot + 1 == P.nslots ? 0 : slot + 1;
-									load_slot(P.table, slot, hi[u], lo[u], val[u], pi[u]);
-									found = slot_matches<KW>(hi[u], lo[u], key[u]);
-									empty = slot_empty<KW>(hi[u], lo[u]);
-								} while (!found && !empty);
-							}
-							if (found) {
-								have_seed = true;
-								seed_pi = pi[u];
-								seed_p = sp[u];
-								seed_fc = fc[u];
-							}
+					uint64_t hi0 = 0, lo0 = 0, pi0 = 0, hi1 = 0, lo1 = 0, pi1 = 0;
+					uint32_t val0 = 0, val1 = 0;
+					if (act0)
+						load_slot(P.table, slot0, hi0, lo0, val0, pi0);
+					if (act1)
+						load_slot(P.table, slot1, hi1, lo1, val1, pi1);
+					if (act0) {
+						bool found = slot_matches<KW>(hi0, lo0, key0);
+						if (!found && !slot_empty<KW>(hi0, lo0)) {
+							const ChainResult cr = slot_chain_find<KW>(P.table, P.nslots, slot0, key0.hi, key0.lo);
+							found = cr.found != 0;
+							pi0 = cr.posinfo;
+						}
+						if (found) {
+							have_seed = true;
+							seed_pi = pi0;
+							seed_p = sp0;
+							seed_fc = fc0;
+						}
+					}
+					if (act1 && !have_seed) {
+						bool found = slot_matches<KW>(hi1, lo1, key1);
+						if (!found && !slot_empty<KW>(hi1, lo1)) {
+							const ChainResult cr = slot_chain_find<KW>(P.table, P.nslots, slot1, key1.hi, key1.lo);
+							found = cr.found != 0;
+							pi1 = cr.posinfo;
+						}
+						if (found) {
+							have_seed = true;
+							seed_pi = pi1;
+							seed_p = sp1;
+							seed_fc = fc1;
 						}
 					}
 				}
@@ -1141,9 +1218,9 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 										Bm[i] |= v;
 									}
 									Pm[nmw] = 0u;
-									dilate_row(Pm, nmw, P.k);
+									dilate_row_call(Pm, nmw, P.k);
 								}
-								dilate_row(Bm, nmw, P.k);
+								dilate_row_call(Bm, nmw, P.k);
 							}
 							// windows in text orientation, 32 at a time
 							const uint64_t w0 = (uint64_t)gw0 >> 5;
@@ -1188,6 +1265,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 		const uint32_t my_lookups = classified ? n_lookup : 0u; // chunks
 		if (__ballot_sync(0xFFFFFFFFu, my_lookups != 0)) {
 			uint32_t incl_l = my_lookups;
+#pragma unroll 1
 			for (int o = 1; o < 32; o <<= 1) {
 				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl_l, o);
 				if (lane >= (uint32_t)o)
@@ -1291,28 +1369,27 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 					for (uint32_t i = lane; i < n_pos; i += 32) {
 						const uint32_t e = G.pos[i];
 						const uint32_t r = e >> 8;
-						bool fc;
-						const Key128 key = canonical_from_forward<KW>(extract_window<KW>(G.W[r], e & 255u, P.mask_hi, P.mask_lo), P.k, &fc);
-						uint64_t slot = hash_to_slot(key_hash<KW>(key), P.nslots);
-						while (true) {
-							uint64_t hi, lo, pi;
-							uint32_t val;
-							load_slot(P.table, slot, hi, lo, val, pi);
-							if (slot_matches<KW>(hi, lo, key)) {
-								atomicAdd(&G.pcnt[r], val ? 0x10001u : 1u);
-								if (val && val != G.rcend[r]) {
-									// a vote for another contig end: one more candidate is tracked
-									const uint32_t old = atomicCAS(&G.rcend2[r], 0u, val);
-									if (old == 0u || old == val)
-										atomicAdd(&G.pcnt2[r], 1u);
-									else
-										atomicOr(&G.pcnt2[r], 0x80000000u);
-								}
-								break;
+						const KeyHash kh = window_key_hash<KW>(G.W[r], e & 255u, P.k, P.mask_hi, P.mask_lo);
+						const uint64_t slot = hash_to_slot(kh.hash, P.nslots);
+						uint64_t hi, lo, pi;
+						uint32_t val;
+						load_slot(P.table, slot, hi, lo, val, pi);
+						bool found = slot_matches<KW>(hi, lo, kh.key);
+						if (!found && !slot_empty<KW>(hi, lo)) {
+							const ChainResult cr = slot_chain_find<KW>(P.table, P.nslots, slot, kh.key.hi, kh.key.lo);
+							found = cr.found != 0;
+							val = cr.val;
+						}
+						if (found) {
+							atomicAdd(&G.pcnt[r], val ? 0x10001u : 1u);
+							if (val && val != G.rcend[r]) {
+								// a vote for another contig end: one more candidate is tracked
+								const uint32_t old = atomicCAS(&G.rcend2[r], 0u, val);
+								if (old == 0u || old == val)
+									atomicAdd(&G.pcnt2[r], 1u);
+								else
+									atomicOr(&G.pcnt2[r], 0x80000000u);
 							}
-							if (slot_empty<KW>(hi, lo))
-								break;
-							slot = slot + 1 == P.nslots ? 0 : slot + 1;
 						}
 					}
 					__syncwarp();
@@ -1395,7 +1472,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 				stored++;
 				out = c_read;
 				const uint32_t cc = (P.remap && out < P.n_remap) ? P.remap[out] : out;
-				imap_add(P.imap, P.imap_mask, P.imap_count, P.barcode_id[my_pair], (cc - 1) >> 1, (cc & 1u), (cc & 1u) ^ 1u);
+				imap_add_call(P.imap, P.imap_mask, P.imap_count, P.barcode_id[my_pair], (cc - 1) >> 1, (cc & 1u), (cc & 1u) ^ 1u);
 			} else {
 				nogood++;
 			}

@@ -12,7 +12,13 @@
 //    the reads are counted in a separate first pass exactly as the reference does.
 //  * -t is accepted and ignored (the GPU does the mapping); --gpus N (or ARKS_GPUS) shards
 //    read pairs by barcode across N GPUs.
-//  * -D (distance estimation) and the alignment (non --arks) mode are not implemented.
+//  * -D (distance estimation, Arcs/DistanceEst.h) runs on the host over the IndexMap rows exported by
+//    the GPU.  Two of its results depend on the iteration order of std::unordered_map containers in the
+//    reference (which intra-contig sample survives when two contigs have the same barcode Jaccard index,
+//    and the line order of --samples_tsv); the same containers are filled in the same order here
+//    (barcodes in the order their first pair was stored, which the GPU reports per pair under -D), so
+//    the output equals the reference's at -t 1 built with the same libstdc++.
+//  * the alignment (non --arks) mode is not implemented.
 #include "../../include/arks_b200.h"
 #include "seq_reader.h"
 
@@ -344,9 +350,16 @@ struct Gpu
 		uint32_t* bc = nullptr;
 		uint64_t n_bases = 0;
 		uint32_t n_pairs = 0;
+		int32_t* out = nullptr;    // -D only: the contig end each pair was stored under (0: not stored)
+		std::vector<uint64_t> seq; // -D only: position of each pair in the input
 	} batch[2];
 	int cur = 0;
 };
+
+// -D: position in the input of the first STORED pair of each barcode = the order in which the reference
+// inserts barcodes into its IndexMap (Arcs.cpp:1280-1285)
+std::vector<uint64_t> g_first_stored;
+uint64_t g_pair_seq = 0;
 
 constexpr uint64_t kBatchBases = 256ull << 20;
 constexpr uint32_t kBatchPairs = 1u << 20;
@@ -365,7 +378,17 @@ void flush_batch(Gpu& g)
 	if (b.n_pairs == 0)
 		return;
 	b.off[2 * b.n_pairs] = (uint32_t)b.n_bases;
-	ck(g.h, arks_map_pairs(g.h, b.bases, b.off, b.bc, b.n_pairs, params.j_index, nullptr), "arks_map_pairs");
+	ck(g.h, arks_map_pairs(g.h, b.bases, b.off, b.bc, b.n_pairs, params.j_index, b.out), "arks_map_pairs");
+	if (b.out) { // the call is synchronous when it returns per-pair results
+		for (uint32_t i = 0; i < b.n_pairs; ++i)
+			if (b.out[i] != 0) {
+				const uint32_t id = b.bc[i];
+				if (id >= g_first_stored.size())
+					g_first_stored.resize((size_t)id + 1 + g_first_stored.size() / 2, UINT64_MAX);
+				g_first_stored[id] = std::min(g_first_stored[id], b.seq[i]);
+			}
+		b.seq.clear();
+	}
 	g.cur ^= 1;
 	g.batch[g.cur].n_pairs = 0;
 	g.batch[g.cur].n_bases = 0;
@@ -387,6 +410,9 @@ void add_pair(Gpu& g, const std::string& s1, const std::string& s2, uint32_t bar
 	memcpy(b->bases + b->n_bases, s2.data(), s2.size());
 	b->n_bases += s2.size();
 	b->bc[b->n_pairs] = barcode;
+	if (b->out)
+		b->seq.push_back(g_pair_seq);
+	g_pair_seq++;
 	b->n_pairs++;
 }
 
@@ -394,12 +420,276 @@ void add_pair(Gpu& g, const std::string& s1, const std::string& s2, uint32_t bar
 struct Edge
 {
 	int u, v, orientation, weight;
+	// EdgeProperties' defaults (Arcs/Arcs.h:166-182); set by -D
+	int minDist = INT_MIN, dist = INT_MAX, maxDist = INT_MAX;
+	float jaccard = -1.0f;
 };
 struct Graph
 {
 	std::vector<std::string> vid; // vertex -> contig name
 	std::vector<Edge> edges;      // in pmap order
 };
+
+// ---- -D: distance estimation (Arcs/DistanceEst.h) over the exported IndexMap rows ----------------
+struct DistSample // DistanceEst.h:37-53
+{
+	unsigned distance = UINT_MAX, barcodesHead = 0, barcodesTail = 0, barcodesUnion = 0, barcodesIntersect = 0;
+};
+struct BarcodeStats // DistanceEst.h:64-78
+{
+	unsigned barcodes1 = 0, barcodes2 = 0, barcodesUnion = 0, barcodesIntersect = 0;
+};
+
+struct DistInput
+{
+	const std::vector<uint32_t>&im_bc, &im_ct, &im_h, &im_t; // IndexMap rows: barcode, contig, head count, tail count
+	const std::vector<std::string>& bc_name;
+	const std::vector<int32_t>& bc_mult;
+	const std::vector<std::string>& ct_name;
+	const std::unordered_map<std::string, int>& to_length;
+	const std::vector<uint32_t>& lexrank;
+	const std::vector<uint64_t>& first_stored;
+};
+
+// quantile (Common/StatUtil.h:9-33), including its weighting (the element BEFORE the boundary gets
+// the fractional part)
+double quantile(const std::vector<unsigned>& v, double q)
+{
+	const size_t lastPos = v.size() - 1;
+	const size_t beforePos = (size_t)floor(q * lastPos);
+	const size_t before = v[beforePos];
+	const size_t afterPos = (size_t)ceil(q * lastPos);
+	const size_t after = v[afterPos];
+	const double weight = (q * lastPos - beforePos) / 1.0;
+	return weight * before + (1.0 - weight) * after;
+}
+
+void calc_distance_estimates(const DistInput& in, Graph& g)
+{
+	const size_t n_rows = in.im_bc.size();
+	const unsigned two_e = (unsigned)2 * params.end_length;
+	// rows grouped by barcode, each barcode's rows in ScafMap order (contig name under std::string '<';
+	// per contig the tail entry (name, false) comes before the head entry (name, true))
+	std::vector<uint32_t> rows(n_rows);
+	for (size_t i = 0; i < n_rows; ++i)
+		rows[i] = (uint32_t)i;
+	std::sort(rows.begin(), rows.end(), [&](uint32_t a, uint32_t b) {
+		return in.im_bc[a] != in.im_bc[b] ? in.im_bc[a] < in.im_bc[b] : in.lexrank[in.im_ct[a]] < in.lexrank[in.im_ct[b]];
+	});
+	std::unordered_map<uint32_t, std::pair<size_t, size_t>> range_of; // barcode -> [first, last) in rows
+	for (size_t i = 0; i < n_rows;) {
+		size_t j = i;
+		while (j < n_rows && in.im_bc[rows[j]] == in.im_bc[rows[i]])
+			++j;
+		range_of[in.im_bc[rows[i]]] = std::make_pair(i, j);
+		i = j;
+	}
+	// the reference iterates its IndexMap, a std::unordered_map<std::string, ...> whose keys were inserted in
+	// the order barcodes first had a pair stored: same container, same insertion order, same iteration order
+	std::vector<uint32_t> present;
+	for (const auto& kv : range_of)
+		present.push_back(kv.first);
+	std::sort(present.begin(), present.end(), [&](uint32_t a, uint32_t b) {
+		const uint64_t fa = a < in.first_stored.size() ? in.first_stored[a] : UINT64_MAX;
+		const uint64_t fb = b < in.first_stored.size() ? in.first_stored[b] : UINT64_MAX;
+		return fa != fb ? fa < fb : a < b;
+	});
+	std::unordered_map<std::string, uint32_t> imap_shadow;
+	for (uint32_t b : present)
+		imap_shadow.emplace(in.bc_name[b], b);
+	std::vector<uint32_t> bc_order;
+	for (const auto& kv : imap_shadow)
+		bc_order.push_back(kv.second);
+
+	auto length_of = [&](uint32_t contig) { return (unsigned)in.to_length.at(in.ct_name[contig]); };
+	auto in_mult_range = [&](uint32_t b) { return !(in.bc_mult[b] < params.min_mult || in.bc_mult[b] > params.max_mult); };
+
+	// ---- calcDistSamples (DistanceEst.h:101-172)
+	std::cout << "\n\t=> Measuring intra-contig distances / shared barcodes... " << stamp();
+	std::unordered_map<std::string, DistSample> distSamples;
+	for (uint32_t b : bc_order) {
+		if (!in_mult_range(b))
+			continue;
+		const auto rg = range_of[b];
+		for (size_t i = rg.first; i < rg.second; ++i) {
+			const uint32_t row = rows[i], contig = in.im_ct[row];
+			for (int isHead = 0; isHead < 2; ++isHead) {
+				const int readPairs = (int)(isHead ? in.im_h[row] : in.im_t[row]);
+				if (readPairs < params.min_reads)
+					continue;
+				const unsigned l = length_of(contig);
+				if (l < two_e)
+					continue;
+				DistSample& s = distSamples[in.ct_name[contig]];
+				s.distance = l - 2 * params.end_length;
+				if (isHead)
+					s.barcodesHead++;
+				else
+					s.barcodesTail++;
+				const bool foundOther = (int)(isHead ? in.im_t[row] : in.im_h[row]) >= params.min_reads;
+				if (foundOther && isHead) {
+					s.barcodesIntersect++;
+					s.barcodesUnion++;
+				} else if (!foundOther) {
+					s.barcodesUnion++;
+				}
+			}
+		}
+	}
+	// ---- writeDistSamplesTSV (DistanceEst.h:501-535)
+	std::cout << "\n\t=> Writing intra-contig distance samples to TSV... " << stamp();
+	if (!params.dist_samples_tsv.empty()) {
+		std::ofstream out(params.dist_samples_tsv.c_str());
+		out << "contig_id" << '\t' << "distance" << '\t' << "barcodes_head" << '\t' << "barcodes_tail" << '\t' << "barcodes_union" << '\t'
+		    << "barcodes_intersect" << '\n';
+		for (const auto& it : distSamples)
+			out << it.first << '\t' << it.second.distance << '\t' << it.second.barcodesHead << '\t' << it.second.barcodesTail << '\t'
+			    << it.second.barcodesUnion << '\t' << it.second.barcodesIntersect << '\n';
+	}
+	// ---- buildJaccardToDist (DistanceEst.h:181-189): the first sample inserted under a Jaccard value stays
+	std::cout << "\n\t=> Building Jaccard to distance map... " << stamp();
+	std::map<double, DistSample> jaccardToDist;
+	for (const auto& it : distSamples)
+		jaccardToDist.insert(std::make_pair(double(it.second.barcodesIntersect) / it.second.barcodesUnion, it.second));
+
+	// ---- buildPairToBarcodeStats (DistanceEst.h:220-334), for the contig pairs that are edges of g
+	std::cout << "\n\t=> Calculating barcode stats for scaffold pairs... " << stamp();
+	std::unordered_map<std::string, uint32_t> contig_of; // name -> first contig with that name
+	for (uint32_t i = 0; i < in.ct_name.size(); ++i)
+		contig_of.emplace(in.ct_name[i], i);
+	struct PairStats
+	{
+		bool present = false;
+		unsigned intersect[4] = { 0, 0, 0, 0 };
+	};
+	std::unordered_map<uint64_t, size_t> edge_of; // (contig a << 32 | contig b) -> edge index
+	std::vector<PairStats> pstats(g.edges.size());
+	for (size_t e = 0; e < g.edges.size(); ++e)
+		edge_of[((uint64_t)contig_of.at(g.vid[g.edges[e].u]) << 32) | contig_of.at(g.vid[g.edges[e].v])] = e;
+	std::vector<unsigned> end_barcodes(2 * in.ct_name.size(), 0); // contigEndToBarcodeCount[2 * contig + isHead]
+	std::vector<std::pair<uint32_t, int>> valid; // (contig, isHead) entries of one barcode that pass validBarcodeMapping
+	for (uint32_t b : bc_order) {
+		if (!in_mult_range(b))
+			continue;
+		const auto rg = range_of[b];
+		valid.clear();
+		for (size_t i = rg.first; i < rg.second; ++i) {
+			const uint32_t row = rows[i], contig = in.im_ct[row];
+			if (length_of(contig) < two_e)
+				continue;
+			for (int isHead = 0; isHead < 2; ++isHead)
+				if ((int)(isHead ? in.im_h[row] : in.im_t[row]) >= params.min_reads) {
+					valid.emplace_back(contig, isHead);
+					end_barcodes[2 * (size_t)contig + isHead]++;
+				}
+		}
+		for (const auto& e1 : valid)
+			for (const auto& e2 : valid) {
+				if (in.lexrank[e1.first] >= in.lexrank[e2.first])
+					continue; // id1 > id2 is skipped upstream; id1 == id2 is never an edge
+				auto it = edge_of.find(((uint64_t)e1.first << 32) | e2.first);
+				if (it == edge_of.end())
+					continue;
+				PairStats& ps = pstats[it->second];
+				ps.present = true;
+				ps.intersect[2 * (e1.second ? 0 : 1) + (e2.second ? 0 : 1)]++;
+			}
+	}
+	auto stats_of = [&](size_t e) {
+		const Edge& ed = g.edges[e];
+		BarcodeStats st;
+		const int i = ed.orientation;
+		st.barcodesIntersect = pstats[e].intersect[i];
+		const uint32_t a = contig_of.at(g.vid[ed.u]), b = contig_of.at(g.vid[ed.v]);
+		const unsigned c1 = end_barcodes[2 * (size_t)a + ((i == 0 || i == 1) ? 1 : 0)];
+		if (c1 == 0)
+			return st;
+		st.barcodes1 = c1;
+		const unsigned c2 = end_barcodes[2 * (size_t)b + ((i == 0 || i == 2) ? 1 : 0)];
+		if (c2 == 0)
+			return st;
+		st.barcodes2 = c2;
+		st.barcodesUnion = st.barcodes1 + st.barcodes2 - st.barcodesIntersect;
+		return st;
+	};
+
+	// ---- addEdgeDistances / estimateDistance (DistanceEst.h:337-430; closestKeys: Common/MapUtil.h:50-95)
+	std::cout << "\n\t=> Adding edge distances... " << stamp();
+	std::vector<std::pair<double, unsigned>> J; // (jaccard, distance), ascending
+	for (const auto& it : jaccardToDist)
+		J.emplace_back(it.first, it.second.distance);
+	if (!J.empty())
+		for (size_t e = 0; e < g.edges.size(); ++e) {
+			if (!pstats[e].present)
+				continue;
+			const BarcodeStats st = stats_of(e);
+			if (st.barcodesUnion == 0)
+				continue;
+			const double jac = double(st.barcodesIntersect) / st.barcodesUnion;
+			// closestKey
+			size_t it = std::lower_bound(J.begin(), J.end(), jac, [](const std::pair<double, unsigned>& x, double k) { return x.first < k; }) -
+			            J.begin();
+			size_t first;
+			if (it == 0)
+				first = 0;
+			else if (it == J.size())
+				first = J.size() - 1;
+			else
+				first = fabs(jac - J[it - 1].first) > fabs(jac - J[it].first) ? it : it - 1;
+			size_t last = first + 1;
+			for (size_t count = 1; count < params.dist_bin_size; ++count) {
+				if (first == 0 && last == J.size())
+					break;
+				if (first == 0)
+					++last;
+				else if (last == J.size())
+					--first;
+				else if (fabs(jac - J[first - 1].first) < fabs(jac - J[last].first))
+					--first;
+				else
+					++last;
+			}
+			std::vector<unsigned> distances;
+			for (size_t i = first; i < last; ++i)
+				distances.push_back(J[i].second);
+			std::sort(distances.begin(), distances.end());
+			Edge& ed = g.edges[e];
+			ed.minDist = (int)floor(quantile(distances, 0.01));
+			ed.dist = (int)round(quantile(distances, 0.5));
+			ed.maxDist = (int)ceil(quantile(distances, 0.99));
+			ed.jaccard = (float)jac;
+		}
+	// ---- writeDistTSV (DistanceEst.h:433-493)
+	if (!params.dist_tsv.empty()) {
+		std::cout << "\n\t=> Writing distance estimates to TSV... " << stamp();
+		std::ofstream out(params.dist_tsv.c_str());
+		out << "contig1" << '\t' << "contig2" << '\t' << "min_dist" << '\t' << "dist" << '\t' << "max_dist" << '\t' << "barcodes1" << '\t'
+		    << "barcodes2" << '\t' << "barcodes_union" << '\t' << "barcodes_intersect" << '\n';
+		for (size_t e = 0; e < g.edges.size(); ++e) {
+			if (!pstats[e].present)
+				continue;
+			const Edge& ed = g.edges[e];
+			const BarcodeStats st = stats_of(e);
+			const bool sense1 = ed.orientation < 2, sense2 = ed.orientation % 2;
+			const std::string &id1 = g.vid[ed.u], &id2 = g.vid[ed.v];
+			for (int pass = 0; pass < 2; ++pass) {
+				if (pass == 0)
+					out << id1 << (sense1 ? '-' : '+') << '\t' << id2 << (sense2 ? '-' : '+') << '\t';
+				else
+					out << id2 << (sense2 ? '+' : '-') << '\t' << id1 << (sense1 ? '+' : '-') << '\t';
+				if (ed.jaccard >= 0)
+					out << ed.minDist << '\t' << ed.dist << '\t' << ed.maxDist << '\t';
+				else
+					out << "NA" << '\t' << "NA" << '\t' << "NA" << '\t';
+				if (pass == 0)
+					out << st.barcodes1 << '\t' << st.barcodes2;
+				else
+					out << st.barcodes2 << '\t' << st.barcodes1;
+				out << '\t' << st.barcodesUnion << '\t' << st.barcodesIntersect << '\n';
+			}
+		}
+	}
+}
 
 } // namespace
 
@@ -493,10 +783,6 @@ int main(int argc, char** argv)
 	if (!params.arks) {
 		std::cerr << PROGRAM ": error: this build implements the k-mer method only: pass --arks (alignment mode is not "
 		                     "part of the B200 hot path).\n";
-		dieflag = true;
-	}
-	if (params.dist_est) {
-		std::cerr << PROGRAM ": error: -D/--dist_est (distance estimation) is not implemented in this build.\n";
 		dieflag = true;
 	}
 	{
@@ -652,6 +938,11 @@ int main(int argc, char** argv)
 			if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
 				die("error: cannot allocate pinned host memory");
 			b.bc = (uint32_t*)p;
+			if (params.dist_est) {
+				if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
+					die("error: cannot allocate pinned host memory");
+				b.out = (int32_t*)p;
+			}
 		}
 	}
 	const double t_index1 = now();
@@ -923,6 +1214,13 @@ int main(int argc, char** argv)
 		}
 	}
 
+	// ---- calcDistanceEstimates (Arcs.cpp:1769-1807, Arcs/DistanceEst.h)
+	if (params.dist_est) {
+		std::cout << "\n=> Calculating distance estimates... " << stamp();
+		DistInput in{ im_bc, im_ct, im_h, im_t, bc.name, bc.mult, ct.name, ct.to_length, lexrank, g_first_stored };
+		calc_distance_estimates(in, g);
+	}
+
 	// ---- writePostRemovalGraph / removeDegreeNodes / writeGraph (Arcs.cpp:1549-1610)
 	std::cout << "\n=> Writing graph file... " << stamp() << "\n";
 	const std::string graphFile = params.base_name + "_original.gv";
@@ -942,8 +1240,12 @@ int main(int argc, char** argv)
 			}
 		std::vector<Edge> ne;
 		for (const auto& e : g.edges)
-			if (remap[e.u] >= 0 && remap[e.v] >= 0)
-				ne.push_back(Edge{ remap[e.u], remap[e.v], e.orientation, e.weight });
+			if (remap[e.u] >= 0 && remap[e.v] >= 0) {
+				Edge n = e;
+				n.u = remap[e.u];
+				n.v = remap[e.v];
+				ne.push_back(n);
+			}
 		g.vid.swap(nv);
 		g.edges.swap(ne);
 	} else {
@@ -957,8 +1259,12 @@ int main(int argc, char** argv)
 		out << "graph G {\n";
 		for (size_t i = 0; i < g.vid.size(); ++i)
 			out << i << " [id=" << g.vid[i] << "];\n";
-		for (const auto& e : g.edges)
-			out << e.u << "--" << e.v << " [label=" << e.orientation << ", weight=" << e.weight << "];\n";
+		for (const auto& e : g.edges) {
+			out << e.u << "--" << e.v << " [label=" << e.orientation << ", weight=" << e.weight;
+			if (e.minDist != INT_MIN) // EdgePropertyWriter, Arcs/Arcs.h:204-211
+				out << ", d=" << e.dist << ", maxd=" << e.maxDist;
+			out << "];\n";
+		}
 		out << "}\n";
 	}
 	const double t_gv = now();
@@ -983,6 +1289,7 @@ int main(int argc, char** argv)
 		{
 			size_t to;
 			int n;
+			int d;
 		};
 		std::vector<std::vector<Out>> adj(vname.size());
 		auto has_edge = [&](size_t u, size_t v) {
@@ -998,10 +1305,12 @@ int main(int argc, char** argv)
 				std::cerr << "error: Duplicate edge: \"" << vname[u] << "\" -> \"" << vname[v] << '"' << std::endl;
 				exit(EXIT_FAILURE);
 			}
-			adj[u].push_back(Out{ v, e.weight });
+			// ep.distance: the fixed gap, or under -D the estimate (INT_MAX where there is none), Arcs.cpp:1635-1648
+			const int d = params.dist_est ? (params.dist_upper ? e.maxDist : e.dist) : (int)params.gap;
+			adj[u].push_back(Out{ v, e.weight, d });
 			const size_t uc = u ^ 1, vc = v ^ 1;
 			if (!(vc == u && uc == v))
-				adj[vc].push_back(Out{ uc, e.weight });
+				adj[vc].push_back(Out{ uc, e.weight, d });
 		}
 		std::ofstream out(params.dist_graph_name.c_str());
 		if (!out)
@@ -1011,7 +1320,7 @@ int main(int argc, char** argv)
 			out << '"' << vname[i] << "\" [l=" << vlen[i] << "]\n";
 		for (size_t u = 0; u < vname.size(); ++u)
 			for (const auto& o : adj[u])
-				out << '"' << vname[u] << "\" -> \"" << vname[o.to] << "\" [d=" << (int)params.gap << " e=" << std::fixed
+				out << '"' << vname[u] << "\" -> \"" << vname[o.to] << "\" [d=" << o.d << " e=" << std::fixed
 				    << std::setprecision(1) << (float)params.gap << " n=" << o.n << "]\n";
 		out << "}\n";
 	}
@@ -1094,6 +1403,8 @@ int main(int argc, char** argv)
 			arks_host_free(b.bases);
 			arks_host_free(b.off);
 			arks_host_free(b.bc);
+			if (b.out)
+				arks_host_free(b.out);
 		}
 		arks_destroy(gp.h);
 	}

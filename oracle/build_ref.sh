@@ -46,6 +46,11 @@ chk Arcs/Arcs.cpp 1133 'chromiumRead'
 chk Arcs/Arcs.cpp 1379 'pairContigs'
 chk Arcs/Arcs.cpp 1460 'checkSignificance'
 chk Arcs/Arcs.cpp 1710 'writeTSV'
+chk Arcs/DistanceEst.h 16 'struct DistanceEstimate'
+chk Arcs/DistanceEst.h 102 'calcDistSamples'
+chk Arcs/DistanceEst.h 338 'estimateDistance'
+chk Arcs/DistanceEst.h 389 '^}'
+chk Arcs/DistanceEst.h 502 'writeDistSamplesTSV'
 
 x() { sed -n "${2},${3}p" "$REF/$1"; }
 { x Arcs/Arcs.h 29 128; } > "$TMP/ref_types.inc"          # namespace ARCS { ... (driver closes it)
@@ -53,6 +58,10 @@ x() { sed -n "${2},${3}p" "$REF/$1"; }
   x Arcs/Arcs.cpp 316 331; x Arcs/Arcs.cpp 363 389; x Arcs/Arcs.cpp 391 547;
   x Arcs/Arcs.cpp 814 830; x Arcs/Arcs.cpp 832 1014; } > "$TMP/ref_part_a.inc"
 { x Arcs/Arcs.cpp 1015 1370; x Arcs/Arcs.cpp 1372 1467; x Arcs/Arcs.cpp 1674 1757; } > "$TMP/ref_part_b.inc"
+# -D distance estimation: everything of Arcs/DistanceEst.h that does not touch the Boost graph
+# (types, calcDistSamples, buildJaccardToDist, buildPairToBarcodeStats, estimateDistance, the
+# samples writer); addEdgeDistances / writeDistTSV are restated over the driver's own graph
+{ x Arcs/DistanceEst.h 15 389; x Arcs/DistanceEst.h 495 535; } > "$TMP/ref_dist.inc"
 
 g++ -std=c++11 -O2 -fopenmp -w -I"$TMP" -I"$REF" -I"$REF/Common" -I"$REF/Arcs" \
     "$HERE/ref_driver.cpp" "$REF/Common/ReadsProcessor.cpp" -lz -o "$OUT/arcs_ref"

@@ -7,7 +7,10 @@
 // the intermediate containers (kmap / per-read conreci trace / imap / pmap), phase
 // timing for the CPU baseline, and a Boost-free restatement of createGraph +
 // boost::write_graphviz (Arcs.cpp:1475-1526,1549-1610; text format pinned by
-// Examples/arks_test-demo/output/*_original.gv).
+// Examples/arks_test-demo/output/*_original.gv).  -D: the distance-estimation functions of
+// Arcs/DistanceEst.h are the reference's own (ref_dist.inc); only the two that walk the Boost graph
+// (addEdgeDistances :392-430, writeDistTSV :433-493) and the edge writer (Arcs.h:185-211) are
+// restated here over RefGraph.
 #include <algorithm>
 #include <cassert>
 #include <chrono>
@@ -33,8 +36,13 @@
 #include <zlib.h>
 
 #include "Common/IOUtil.h"
+#include "Common/MapUtil.h"
+#include "Common/PairHash.h"
 #include "Common/ReadsProcessor.h"
+#include "Common/StatUtil.h"
 #include "kseq.h"
+#include <array>
+using std::ofstream;
 
 #include "ref_types.inc" // opens namespace ARCS, ArcsParams .. ContigToLengthIt
 // google::sparse_hash_map stand-in.  The reference only ever find()s / operator[]s
@@ -62,11 +70,17 @@ bestContig_traced(ARCS::ContigKMap& kmap, std::string readseq, int k, double j, 
 #define bestContig bestContig_traced
 #include "ref_part_b.inc" // getContigKmers .. checkSignificance, TSV writers
 #undef bestContig
+#include "ref_dist.inc" // DistanceEst.h minus the Boost-graph functions
 
 // ---- Boost-free createGraph / removeDegreeNodes / write_graphviz restatement ----
 struct RefEdge
 {
 	int u, v, orientation, weight;
+	// EdgeProperties' defaults (Arcs.h:166-182)
+	int minDist = std::numeric_limits<int>::min();
+	int dist = std::numeric_limits<int>::max();
+	int maxDist = std::numeric_limits<int>::max();
+	float jaccard = -1.0f;
 };
 struct RefGraph
 {
@@ -91,7 +105,12 @@ createGraphNoBoost(const ARCS::PairMap& pmap, RefGraph& g)
 					vmap[*s] = (int)g.vid.size();
 					g.vid.push_back(*s);
 				}
-			g.edges.push_back({ vmap[it->first.first], vmap[it->first.second], (int)index, (int)max });
+			RefEdge e;
+			e.u = vmap[it->first.first];
+			e.v = vmap[it->first.second];
+			e.orientation = (int)index;
+			e.weight = (int)max;
+			g.edges.push_back(e);
 		}
 	}
 }
@@ -114,8 +133,12 @@ writeGraphNoBoost(const std::string& path, RefGraph g, int max_degree)
 			}
 		std::vector<RefEdge> ne;
 		for (auto& e : g.edges)
-			if (remap[e.u] >= 0 && remap[e.v] >= 0)
-				ne.push_back({ remap[e.u], remap[e.v], e.orientation, e.weight });
+			if (remap[e.u] >= 0 && remap[e.v] >= 0) {
+				RefEdge n = e;
+				n.u = remap[e.u];
+				n.v = remap[e.v];
+				ne.push_back(n);
+			}
 		g.vid.swap(nv);
 		g.edges.swap(ne);
 	}
@@ -123,9 +146,69 @@ writeGraphNoBoost(const std::string& path, RefGraph g, int max_degree)
 	out << "graph G {\n";
 	for (size_t i = 0; i < g.vid.size(); ++i)
 		out << i << " [id=" << g.vid[i] << "];\n";
-	for (auto& e : g.edges)
-		out << e.u << "--" << e.v << " [label=" << e.orientation << ", weight=" << e.weight << "];\n";
+	for (auto& e : g.edges) {
+		out << e.u << "--" << e.v << " [label=" << e.orientation << ", weight=" << e.weight;
+		if (e.minDist != std::numeric_limits<int>::min()) // EdgePropertyWriter, Arcs.h:204-211
+			out << ", d=" << e.dist << ", maxd=" << e.maxDist;
+		out << "];\n";
+	}
 	out << "}\n";
+}
+
+// addEdgeDistances (DistanceEst.h:392-430) over RefGraph
+static void
+addEdgeDistancesNoBoost(const PairToBarcodeStats& pairToStats, const JaccardToDist& jaccardToDist, RefGraph& g)
+{
+	if (jaccardToDist.empty())
+		return;
+	for (auto& e : g.edges) {
+		auto statsIt = pairToStats.find(std::make_pair(g.vid[e.u], g.vid[e.v]));
+		if (statsIt == pairToStats.end())
+			continue;
+		const BarcodeStats& stats = statsIt->second.at(e.orientation);
+		DistanceEstimate est;
+		bool success;
+		std::tie(est, success) = estimateDistance(stats, jaccardToDist, params);
+		if (!success)
+			continue;
+		e.minDist = est.minDist;
+		e.dist = est.dist;
+		e.maxDist = est.maxDist;
+		e.jaccard = est.jaccard;
+	}
+}
+
+// writeDistTSV (DistanceEst.h:433-493) over RefGraph
+static void
+writeDistTSVNoBoost(const std::string& path, const PairToBarcodeStats& pairToStats, const RefGraph& g)
+{
+	std::ofstream tsvOut(path.c_str());
+	tsvOut << "contig1" << '\t' << "contig2" << '\t' << "min_dist" << '\t' << "dist" << '\t' << "max_dist" << '\t'
+	       << "barcodes1" << '\t' << "barcodes2" << '\t' << "barcodes_union" << '\t' << "barcodes_intersect" << '\n';
+	for (auto& e : g.edges) {
+		auto pair = std::make_pair(g.vid[e.u], g.vid[e.v]);
+		auto statsIt = pairToStats.find(pair);
+		if (statsIt == pairToStats.end())
+			continue;
+		const BarcodeStats& stats = statsIt->second.at(e.orientation);
+		bool sense1 = e.orientation < 2;
+		bool sense2 = e.orientation % 2;
+		for (int pass = 0; pass < 2; ++pass) {
+			if (pass == 0)
+				tsvOut << pair.first << (sense1 ? '-' : '+') << '\t' << pair.second << (sense2 ? '-' : '+') << '\t';
+			else
+				tsvOut << pair.second << (sense2 ? '+' : '-') << '\t' << pair.first << (sense1 ? '+' : '-') << '\t';
+			if (e.jaccard >= 0)
+				tsvOut << e.minDist << '\t' << e.dist << '\t' << e.maxDist << '\t';
+			else
+				tsvOut << "NA" << '\t' << "NA" << '\t' << "NA" << '\t';
+			if (pass == 0)
+				tsvOut << stats.barcodes1 << '\t' << stats.barcodes2;
+			else
+				tsvOut << stats.barcodes2 << '\t' << stats.barcodes1;
+			tsvOut << '\t' << stats.barcodesUnion << '\t' << stats.barcodesIntersect << '\n';
+		}
+	}
 }
 
 static std::string
@@ -158,9 +241,13 @@ main(int argc, char** argv)
 		                                { "arks", no_argument, NULL, 1006 },
 		                                { "tsv", required_argument, NULL, 1007 },
 		                                { "barcode-counts", required_argument, NULL, 1008 },
+		                                { "dist_tsv", required_argument, NULL, 1009 },
+		                                { "samples_tsv", required_argument, NULL, 1010 },
+		                                { "dist_est", no_argument, NULL, 'D' },
+		                                { "bin_size", required_argument, NULL, 'B' },
 		                                { NULL, 0, NULL, 0 } };
 	params.arks = true;
-	for (int c; (c = getopt_long(argc, argv, "f:c:l:z:b:m:d:e:r:vt:u:j:k:", lo, NULL)) != -1;) {
+	for (int c; (c = getopt_long(argc, argv, "f:c:l:z:b:m:d:e:r:vt:u:j:k:DB:", lo, NULL)) != -1;) {
 		std::istringstream arg(optarg != NULL ? optarg : "");
 		switch (c) {
 		case 'u': arg >> params.multfile; break;
@@ -192,6 +279,10 @@ main(int argc, char** argv)
 		case 1006: break;
 		case 1007: params.tsv_name = optarg; break;
 		case 1008: params.barcode_counts_name = optarg; break;
+		case 1009: params.dist_tsv = optarg; break;
+		case 1010: params.dist_samples_tsv = optarg; break;
+		case 'D': params.dist_est = true; break;
+		case 'B': arg >> params.dist_bin_size; break;
 		default: return 2;
 		}
 	}
@@ -229,6 +320,18 @@ main(int argc, char** argv)
 	double t4 = now();
 	RefGraph g;
 	createGraphNoBoost(pmap, g);
+	if (params.dist_est) { // calcDistanceEstimates, Arcs.cpp:1769-1807
+		DistSampleMap distSamples;
+		calcDistSamples(imap, contigToLength, indexMultMap, params, distSamples);
+		writeDistSamplesTSV(params.dist_samples_tsv, distSamples);
+		JaccardToDist jaccardToDist;
+		buildJaccardToDist(distSamples, jaccardToDist);
+		PairToBarcodeStats pairToStats;
+		buildPairToBarcodeStats(imap, indexMultMap, contigToLength, params, pairToStats);
+		addEdgeDistancesNoBoost(pairToStats, jaccardToDist, g);
+		if (!params.dist_tsv.empty())
+			writeDistTSVNoBoost(params.dist_tsv, pairToStats, g);
+	}
 	writeGraphNoBoost(params.base_name + "_original.gv", g, params.max_degree);
 	double t5 = now();
 	if (!params.tsv_name.empty()) {

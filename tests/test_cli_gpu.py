@@ -90,6 +90,9 @@ def test_cli_matches_reference_code(argsfile, mode, tmp_path):
             "-P"] + spec["args"]
     if spec["multfile"]:
         args += ["-u", os.path.join(d, spec["multfile"])]
+    dist = "-D" in spec["args"]
+    if dist:  # distance estimation (Arcs/DistanceEst.h): per-edge estimates and the intra-contig samples
+        args += ["--dist_tsv", str(tmp_path / "dist.tsv"), "--samples_tsv", str(tmp_path / "samples.tsv")]
     if mode == "two-pass":
         args.append("--two-pass")
     env_gpus = None
@@ -107,3 +110,12 @@ def test_cli_matches_reference_code(argsfile, mode, tmp_path):
     assert read(tmp_path / "o_main.tsv") == read(exp + "_main.tsv")
     assert read(tmp_path / "o_pair.tsv") == read(exp + "_pmap.txt")
     assert read(tmp_path / "bc.tsv") == read(exp + "_bc.tsv")
+    if dist:
+        assert read(tmp_path / "dist.tsv") == read(exp + "_dist.tsv")
+        assert read(tmp_path / "samples.tsv") == read(exp + "_samples.tsv")
+        # the ABySS graph carries the estimate (or INT_MAX where there is none) instead of the fixed gap
+        est = {ln.split("\t")[3] for ln in read(exp + "_dist.tsv").splitlines()[1:]}
+        want_d = {x for x in est if x != "NA"} | ({"2147483647"} if "NA" in est or " weight=" in "".join(
+            ln for ln in read(exp + "_original.gv").splitlines() if "--" in ln and "d=" not in ln) else set())
+        got_d = {ln.split("[d=")[1].split(" ")[0] for ln in read(tmp_path / "o.dist.gv").splitlines() if " -> " in ln}
+        assert got_d == want_d

@@ -193,6 +193,17 @@ def test_map_pairs_chimeric_noisy_and_boundary_reads(k, j):
     assert idx.map_stats().as_dict() == st.as_dict()
 
 
+def test_map_pairs_dense_table(monkeypatch):
+    """load factor 0.9 (what a draft that nearly fills the GPU gets): long probe sequences in the build, in
+    the seed probes and behind the membership filter"""
+    monkeypatch.setenv("ARKS_TABLE_LOAD", "0.9")
+    k, j = 40, 0.3
+    rng = np.random.default_rng(99)
+    genome, contigs = synth.make_draft(rng, 100000, 7000, k, n_runs=3, dup_frac=0.0)
+    _check_map(k, j, genome, contigs, rng, n_barcodes=30, pairs_per_barcode=30, read_len=150, mol_len=20000,
+               mols_per_barcode=2, sub_rate=0.004, n_rate=0.002, len_jitter=20)
+
+
 def test_pair_links_match_oracle():
     k, j = 30, 0.4
     rng = np.random.default_rng(11)

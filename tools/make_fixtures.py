@@ -105,14 +105,32 @@ def run_ref(d, args, tag, multfile=None):
            "--dump-imap", base + "_imap.txt", "--dump-pmap", base + "_pmap.txt", "--timing-json", base + "_stats.json"] + args
     if multfile:
         cmd += ["-u", multfile]
+    if "-D" in args:  # distance estimation: estimates per edge + the intra-contig samples
+        cmd += ["--dist_tsv", base + "_dist.tsv", "--samples_tsv", base + "_samples.tsv"]
     cmd.append(os.path.join(d, "reads.fq.gz"))
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     json.dump({"args": args, "multfile": os.path.basename(multfile) if multfile else None}, open(base + "_args.json", "w"))
 
 
+def add_dist_cases():
+    """-D runs of the reference's code on the existing inputs (tags d*, added after the first fixtures)"""
+    d = os.path.join(OUT, "mixed_k30")
+    run_ref(d, ["-k", "30", "-j", "0.5", "-c", "3", "-m", "20-10000", "-e", "3000", "-z", "500", "-r", "0.05", "-t", "1", "-D", "-B", "3"],
+            "d")
+    run_ref(d, ["-k", "30", "-j", "0.2", "-c", "2", "-m", "1-1000", "-e", "1500", "-z", "3000", "-r", "0.2", "-l", "2", "-d", "3", "-t", "1",
+                "-D"], "e")
+    d = os.path.join(OUT, "plain_k60")
+    run_ref(d, ["-k", "60", "-j", "0.55", "-c", "5", "-m", "50-10000", "-e", "4000", "-z", "500", "-r", "0.05", "-t", "1", "-D", "-B", "2"],
+            "d")
+    d = os.path.join(OUT, "long_k20")
+    run_ref(d, ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "5000", "-z", "500", "-r", "0.05", "-t", "1", "-D"], "d")
+
+
 def main():
     if not os.path.exists(REF):
         raise SystemExit("oracle/_ref/arcs_ref is missing: run oracle/build_ref.sh where /root/reference exists")
+    if len(sys.argv) > 1 and sys.argv[1] == "dist":
+        return add_dist_cases()
     # case A: k=30 defaults-ish, adversarial FASTQ, contig names whose string order differs from numeric order
     names = ["10", "9", "100", "2", "b", "a", "2", "11", "1", "3"]  # "2" appears twice
     d = make_case("mixed_k30", 11, 30, contig_names=names, fastq_mutator=mutate, n_barcodes=120, ppb=60, mol_len=9000, mols=1)
@@ -132,6 +150,7 @@ def main():
     # case C: k=20, low Jaccard threshold, long-read style pseudo pairs (250 bp)
     d = make_case("long_k20", 13, 20, genome_len=100000, mean_contig=20000, n_barcodes=300, ppb=12, read_len=250, jitter=0, mol_len=15000, mols=1)
     run_ref(d, ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
+    add_dist_cases()
     print("fixtures written under", OUT)
     subprocess.call(["du", "-sh", OUT])
 
