@@ -872,20 +872,32 @@ constexpr int kGroupMStride = kGroupReadBases / 32 + 1; // 9 words: one mask bit
 struct GroupSmem
 {
 	uint32_t W[32][kGroupWStride];
-	uint32_t INV[32][kGroupIStride];
-	uint32_t BM[32][kGroupMStride]; // per read: mismatch/invalid base mask, then "window overlaps one" (text orientation)
+	// the invalid-base / mismatch masks are dead once the windows are classified; the lookup lists of
+	// stage 2b live in the same bytes
+	union Scratch
+	{
+		struct Masks
+		{
+			uint32_t INV[32][kGroupIStride];
+			uint32_t BM[32][kGroupMStride]; // per read: mismatch/invalid base mask, then "window overlaps one" (text orientation)
+		} m;
+		struct Lists
+		{
+			uint16_t list[kGroupListCap]; // staged lookups: read << 11 | first window (text orientation) << 3 | windows - 1
+			uint16_t pos[256];            // filter positives of one round: read << 8 | read window
+			uint32_t npos;
+		} l;
+	} s;
 	uint32_t PM[32][kGroupMStride]; // per read: invalid base mask, then "window overlaps one", then the lookup mask
 	uint32_t woff[33];
-	uint32_t nbad[32];  // per read: N count | other-invalid count << 16
+	uint32_t nbad[32];   // per read: N count | other-invalid count << 16
 	uint32_t rinfo[32];  // per read: number of windows | same-strand flag << 16
 	uint32_t rcend[32];  // per read: the seed's contig end
 	uint32_t rcend2[32]; // per read: a second contig end its lookups voted for (0: none yet)
 	uint32_t pcnt[32];   // per read: lookups found | lookups recorded << 16
 	uint32_t pcnt2[32];  // per read: lookups recorded for rcend2 | (a third contig end turned up) << 31
-	uint16_t list[kGroupListCap]; // staged lookups: read << 11 | first window (text orientation) << 3 | windows - 1
-	uint16_t pos[256];            // filter positives of one round: read << 8 | read window
-	uint32_t npos;
 };
+static_assert(sizeof(GroupSmem::Scratch::Lists) <= sizeof(GroupSmem::Scratch::Masks), "lookup lists must fit in the mask rows");
 
 constexpr uint32_t kChunkWindows = 8; // consecutive windows one lane looks up with a rolling key
 #ifndef ARKS_LOOKUP_BATCH
@@ -1075,7 +1087,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 			const uint32_t rlen = P.read_off[2 * pair0 + r + 1] - roff;
 			uint32_t inv16, nn, no;
 			G.W[r][j] = pack_group_compact(P.bases + roff, rlen, j, &inv16, &nn, &no);
-			reinterpret_cast<uint16_t*>(G.INV[r])[j] = (uint16_t)inv16;
+			reinterpret_cast<uint16_t*>(G.s.m.INV[r])[j] = (uint16_t)inv16;
 			if (inv16)
 				atomicAdd(&G.nbad[r], nn | (no << 16));
 		}
@@ -1115,7 +1127,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 					for (uint32_t u = 0; u < 2; ++u) {
 						const uint32_t sidx = s0 + u;
 						const uint32_t sp = seed_window(sidx, total);
-						const bool act = sidx < (uint32_t)kGroupSeeds && (clean || !window_invalid(G.INV[lane], sp, P.k));
+						const bool act = sidx < (uint32_t)kGroupSeeds && (clean || !window_invalid(G.s.m.INV[lane], sp, P.k));
 						KeyHash kh{{0, 0}, 0, 0};
 						if (act)
 							kh = window_key_hash<KW>(Wr, sp, P.k, P.mask_hi, P.mask_lo);
@@ -1186,7 +1198,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 						const int64_t hi_s = e_hi - (int64_t)P.k - gw0 + 1;
 						const uint32_t u_hi = hi_s <= 0 ? 0u : (uint32_t)min((int64_t)total, hi_s);
 						// the read against the contig text, 16 bases at a time: one mismatch bit per base
-						uint32_t* Bm = G.BM[lane];
+						uint32_t* Bm = G.s.m.BM[lane];
 						uint32_t* Pm = G.PM[lane];
 						const uint32_t nmw = (len + 31) >> 5;
 						for (uint32_t i = 0; i <= nmw; ++i)
@@ -1210,7 +1222,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 									for (uint32_t i = 0; i < nmw; ++i)
 										Bm[i] = __funnelshift_r(Bm[i], Bm[i + 1], q0);
 								if (!clean) {
-									const uint32_t* Ir = G.INV[lane];
+									const uint32_t* Ir = G.s.m.INV[lane];
 									for (uint32_t i = 0; i < nmw; ++i) {
 										const uint32_t v = same ? mask_bits_at(Ir, (int)(32 * i), (int)len)
 										                        : __brev(mask_bits_at(Ir, (int)len - 32 - (int)(32 * i), (int)len));
@@ -1297,7 +1309,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 							const uint32_t c = min(run, kChunkWindows);
 							m &= ~((c >= 32u ? 0xFFFFFFFFu : ((1u << c) - 1u)) << s);
 							if (idx >= base && idx < base + kGroupListCap)
-								G.list[idx - base] = (uint16_t)((lane << 11) | ((32u * w + s) << 3) | (c - 1u));
+								G.s.l.list[idx - base] = (uint16_t)((lane << 11) | ((32u * w + s) << 3) | (c - 1u));
 							idx++;
 						}
 					}
@@ -1309,11 +1321,11 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 					// 32 chunks at a time through the filter; the positives (rare) are collected and consulted
 					// in the table afterwards, all at once, so that their DRAM round trips overlap
 					if (lane == 0)
-						G.npos = 0;
+						G.s.l.npos = 0;
 					__syncwarp();
 					const uint32_t f = f0 + lane;
 					if (f < n_here) {
-						const uint32_t e = G.list[f];
+						const uint32_t e = G.s.l.list[f];
 						const uint32_t r = e >> 11, u0 = (e >> 3) & 255u, n = (e & 7u) + 1u;
 						const uint32_t info = G.rinfo[r];
 						const uint32_t tot = info & 0xFFFFu;
@@ -1359,15 +1371,15 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 #pragma unroll
 							for (int jj = 0; jj < kLookupBatch; ++jj) {
 								if (i0 + jj < n && bloom_test(sel[jj], flo[jj], fhi[jj]))
-									G.pos[atomicAdd(&G.npos, 1u)] = (uint16_t)((r << 8) | (p_lo + i0 + jj));
+									G.s.l.pos[atomicAdd(&G.s.l.npos, 1u)] = (uint16_t)((r << 8) | (p_lo + i0 + jj));
 							}
 						}
 					}
 					__syncwarp();
-					const uint32_t n_pos = G.npos;
+					const uint32_t n_pos = G.s.l.npos;
 #pragma unroll 1
 					for (uint32_t i = lane; i < n_pos; i += 32) {
-						const uint32_t e = G.pos[i];
+						const uint32_t e = G.s.l.pos[i];
 						const uint32_t r = e >> 8;
 						const KeyHash kh = window_key_hash<KW>(G.W[r], e & 255u, P.k, P.mask_hi, P.mask_lo);
 						const uint64_t slot = hash_to_slot(kh.hash, P.nslots);

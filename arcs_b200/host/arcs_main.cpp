@@ -20,6 +20,7 @@
 //    the output equals the reference's at -t 1 built with the same libstdc++.
 //  * the alignment (non --arks) mode is not implemented.
 #include "../../include/arks_b200.h"
+#include "ingest.h"
 #include "seq_reader.h"
 
 #include <algorithm>
@@ -38,6 +39,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unistd.h>
 #include <unordered_map>
 #include <vector>
@@ -45,8 +47,12 @@
 #define PROGRAM "arcs"
 #define PACKAGE_VERSION "1.2.8-b200"
 
+using arks_host::Barcodes;
+using arks_host::count_barcode;
+using arks_host::extract_bx;
 using arks_host::SeqReader;
 using arks_host::SeqRecord;
+using arks_host::strip_read_num;
 
 namespace {
 
@@ -180,31 +186,6 @@ double now()
 
 // ---- small restatements of the reference's helpers -------------------------------------------
 
-// stripReadNum (Arcs.cpp:243-254)
-void strip_read_num(std::string& name)
-{
-	size_t pos = name.rfind('/');
-	if (pos == std::string::npos || pos == 0 || pos == name.length() - 1)
-		return;
-	if (!std::isdigit((unsigned char)name[pos + 1]))
-		return;
-	name.resize(pos);
-}
-
-// barcode = text after the first "BX:Z:" up to the next ' ' (Arcs.cpp:1227-1251)
-void extract_bx(const std::string& comment, std::string& barcode)
-{
-	barcode.clear();
-	size_t tag = comment.find("BX:Z:");
-	if (tag == std::string::npos)
-		return;
-	size_t end = comment.find(' ', tag);
-	if (end != std::string::npos)
-		barcode.assign(comment, tag + 5, end - tag - 5);
-	else
-		barcode.assign(comment, tag + 5, std::string::npos);
-}
-
 // readFof (Arcs.cpp:776-794): one file name per whitespace-separated token
 std::vector<std::string> read_fof(const std::string& fof)
 {
@@ -258,27 +239,7 @@ bool check_significance(int max, int second)
 	return (1 - cdf < params.error_percent);
 }
 
-// ---- barcodes ----------------------------------------------------------------------------------
-struct Barcodes
-{
-	std::unordered_map<std::string, uint32_t> id;
-	std::vector<std::string> name;
-	std::vector<int32_t> mult;    // indexMultMap value
-	std::vector<uint8_t> counted; // the barcode is a key of indexMultMap
-	uint32_t intern(const std::string& b)
-	{
-		auto it = id.find(b);
-		if (it != id.end())
-			return it->second;
-		uint32_t i = (uint32_t)name.size();
-		id.emplace(b, i);
-		name.push_back(b);
-		mult.push_back(0);
-		counted.push_back(0);
-		return i;
-	}
-};
-
+// ---- barcodes (struct Barcodes: ingest.h) -----------------------------------------------------------
 // createIndexMultMap (Arcs.cpp:392-448)
 void load_multfile(const std::string& path, Barcodes& bc)
 {
@@ -312,20 +273,6 @@ void load_multfile(const std::string& path, Barcodes& bc)
 	}
 	if (params.verbose)
 		std::cout << "Saw " << n << "  distinct barcodes." << std::endl;
-}
-
-// readBarcodes' counting rule for one record (Arcs.cpp:514-537): call for every record of a
-// file until the first one with l <= 0
-void count_barcode(const SeqRecord& r, Barcodes& bc, std::string& scratch)
-{
-	if (r.comment.empty())
-		return;
-	if (r.comment.find("BX:Z:") == std::string::npos)
-		return;
-	extract_bx(r.comment, scratch);
-	uint32_t i = bc.intern(scratch);
-	bc.mult[i]++;
-	bc.counted[i] = 1;
 }
 
 // ---- contigs -----------------------------------------------------------------------------------
@@ -394,21 +341,21 @@ void flush_batch(Gpu& g)
 	g.batch[g.cur].n_bases = 0;
 }
 
-void add_pair(Gpu& g, const std::string& s1, const std::string& s2, uint32_t barcode)
+void add_pair(Gpu& g, const char* s1, size_t l1, const char* s2, size_t l2, uint32_t barcode)
 {
-	if (s1.size() + s2.size() > kBatchBases / 2)
+	if (l1 + l2 > kBatchBases / 2)
 		die("error: read pair longer than the batch buffer");
 	Gpu::Batch* b = &g.batch[g.cur];
-	if (b->n_pairs >= kBatchPairs || b->n_bases + s1.size() + s2.size() > kBatchBases) {
+	if (b->n_pairs >= kBatchPairs || b->n_bases + l1 + l2 > kBatchBases) {
 		flush_batch(g);
 		b = &g.batch[g.cur];
 	}
 	b->off[2 * b->n_pairs] = (uint32_t)b->n_bases;
-	memcpy(b->bases + b->n_bases, s1.data(), s1.size());
-	b->n_bases += s1.size();
+	memcpy(b->bases + b->n_bases, s1, l1);
+	b->n_bases += l1;
 	b->off[2 * b->n_pairs + 1] = (uint32_t)b->n_bases;
-	memcpy(b->bases + b->n_bases, s2.data(), s2.size());
-	b->n_bases += s2.size();
+	memcpy(b->bases + b->n_bases, s2, l2);
+	b->n_bases += l2;
 	b->bc[b->n_pairs] = barcode;
 	if (b->out)
 		b->seq.push_back(g_pair_seq);
@@ -960,13 +907,80 @@ int main(int argc, char** argv)
 	// ---- reads: chromiumRead (Arcs.cpp:1132-1351)
 	std::cout << "\n=>Reading Chromium FASTQ file(s)... " << stamp() << std::endl;
 	const double t_map0 = now();
-	size_t skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0, count = 0;
+	size_t skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0;
+	size_t fast_blocks = 0;
 	{
-		SeqRecord r1, r2;
-		std::string b1, b2, n1, n2, scratch;
+		arks_host::IngestConfig cfg;
+		cfg.mult_known = mult_known;
+		cfg.verbose = params.verbose != 0;
+		cfg.min_mult = params.min_mult;
+		cfg.max_mult = params.max_mult;
+		arks_host::IngestCounters ictr;
+		arks_host::PairSink sink;
+		sink.add = [&](const std::string& s1, const std::string& s2, uint32_t id) {
+			add_pair(gpus[id % params.gpus], s1.data(), s1.size(), s2.data(), s2.size(), id);
+		};
+		sink.submit = [&](const arks_host::PairBatch& b) {
+			if (params.gpus == 1) { // the block is already a batch in pinned memory
+				ck(gpus[0].h, arks_map_pairs(gpus[0].h, b.bases, b.off, b.bc, b.n_pairs, params.j_index, nullptr), "arks_map_pairs");
+				return;
+			}
+			for (uint32_t i = 0; i < b.n_pairs; ++i)
+				add_pair(gpus[b.bc[i] % params.gpus], b.bases + b.off[2 * i], b.off[2 * i + 1] - b.off[2 * i], b.bases + b.off[2 * i + 1],
+				    b.off[2 * i + 2] - b.off[2 * i + 1], b.bc[i]);
+		};
+		// block-parallel parsing (ingest.h) unless -D needs the pairs' input order or ARKS_PARSE_THREADS=0
+		arks_host::ParallelIngestOptions popt;
+		popt.workers = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+		if (const char* e = getenv("ARKS_PARSE_THREADS"))
+			popt.workers = atoi(e);
+		if (const char* e = getenv("ARKS_PARSE_BLOCK_MB"))
+			popt.block_bytes = (size_t)std::max(1, atoi(e)) << 20;
+		const bool parallel = popt.workers > 0 && !params.dist_est;
+		std::vector<void*> pinned;
+		if (parallel) {
+			const uint32_t cap_pairs = (uint32_t)(popt.block_bytes / 48 + 16);
+			for (int i = 0; i < popt.workers + 2; ++i) {
+				arks_host::PairBatch pb;
+				void* p;
+				if (arks_host_alloc(&p, popt.block_bytes + 4096) != ARKS_OK)
+					die("error: cannot allocate pinned host memory");
+				pb.bases = (char*)p;
+				pinned.push_back(p);
+				if (arks_host_alloc(&p, (2ull * cap_pairs + 1) * 4) != ARKS_OK)
+					die("error: cannot allocate pinned host memory");
+				pb.off = (uint32_t*)p;
+				pinned.push_back(p);
+				if (arks_host_alloc(&p, cap_pairs * 4ull) != ARKS_OK)
+					die("error: cannot allocate pinned host memory");
+				pb.bc = (uint32_t*)p;
+				pinned.push_back(p);
+				pb.cap_bases = popt.block_bytes;
+				pb.cap_pairs = cap_pairs;
+				popt.slots.push_back(pb);
+			}
+		}
 		for (const auto& f : filenames) {
 			if (params.verbose)
 				std::cout << "Reading chrom " << f << std::endl;
+			bool counting = !mult_known; // readBarcodes stops at the first record with l <= 0
+			if (parallel) {
+				{
+					std::ifstream probe(f.c_str());
+					if (!probe.good()) {
+						std::cerr << "File " << f << " cannot be opened." << std::endl;
+						exit(1);
+					}
+				}
+				std::cerr << "File " << f << " opened." << std::endl;
+				size_t nb = 0;
+				if (!arks_host::ingest_parallel_blocks(f, bc, cfg, counting, ictr, sink, popt, &nb)) {
+					std::cerr << "File " << f << " cannot be opened." << std::endl;
+					exit(1);
+				}
+				fast_blocks += nb;
+				continue;
+			}
 			SeqReader rd(f);
 			if (!rd.ok()) {
 				std::cerr << "File " << f << " cannot be opened." << std::endl;
@@ -974,86 +988,16 @@ int main(int argc, char** argv)
 			} else {
 				std::cerr << "File " << f << " opened." << std::endl;
 			}
-			bool counting = !mult_known; // readBarcodes stops at the first record with l <= 0
-			bool stop = false;
-			while (!stop) {
-				bool paired = false;
-				r1.name.clear();
-				r2.name.clear();
-				r1.comment.clear();
-				r2.comment.clear();
-				int l = rd.read(r1);
-				if (l >= 0) {
-					r1.truncate_at_nul();
-					if (counting) {
-						if (l > 0)
-							count_barcode(r1, bc, scratch);
-						else
-							counting = false;
-					}
-					l = rd.read(r2);
-					if (l >= 0) {
-						r2.truncate_at_nul();
-						if (counting) {
-							if (l > 0)
-								count_barcode(r2, bc, scratch);
-							else
-								counting = false;
-						}
-					} else {
-						r2.name.clear();
-						r2.comment.clear();
-						stop = true;
-					}
-				} else {
-					stop = true;
-				}
-				n1 = r1.name;
-				n2 = stop && l < 0 && r2.name.empty() ? std::string() : r2.name;
-				strip_read_num(n1);
-				strip_read_num(n2);
-				if (n1 == n2) {
-					paired = true;
-				} else {
-					std::cout << "File contains unpaired reads: " << n1 << " " << n2 << std::endl;
-					skipped_unpaired++;
-				}
-				count += 2;
-				if (params.verbose && count % 10000000 == 0)
-					std::cout << "Processed " << count << " read pairs." << std::endl;
-				if (stop)
-					break;
-				extract_bx(r1.comment, b1);
-				extract_bx(r2.comment, b2);
-				if (b1.empty() || b2.empty()) {
-					emptybarcode++;
-					continue;
-				}
-				if (!paired || b1 != b2) {
-					// (the reference still looks barcode1 up here, only to count invalid barcodes)
-					continue;
-				}
-				uint32_t id;
-				if (mult_known) {
-					auto it = bc.id.find(b1);
-					if (it == bc.id.end() || !bc.counted[it->second]) {
-						invalidbarcode++;
-						continue;
-					}
-					id = it->second;
-					const int m = bc.mult[id];
-					if (!(m > params.min_mult || m < params.max_mult)) { // goodmult, Arcs.cpp:1267
-						skipped_badmult++;
-						continue;
-					}
-				} else {
-					id = bc.intern(b1); // validity (is it a key of indexMultMap) is settled after the pass
-				}
-				add_pair(gpus[id % params.gpus], r1.seq, r2.seq, id);
-			}
+			arks_host::ingest_sequential(rd, bc, cfg, counting, ictr, sink);
 		}
 		for (auto& g : gpus)
 			flush_batch(g);
+		for (void* p : pinned)
+			arks_host_free(p);
+		skipped_unpaired = ictr.skipped_unpaired;
+		emptybarcode = ictr.emptybarcode;
+		invalidbarcode = ictr.invalidbarcode;
+		skipped_badmult = ictr.skipped_badmult;
 	}
 	arks_map_stats mst{};
 	for (auto& g : gpus) {
@@ -1082,8 +1026,9 @@ int main(int argc, char** argv)
 			printf("WARNING:: Your chromium read file has %zu read pairs that have barcodes not in the barcode multiplicity file.",
 			    invalidbarcode);
 		const double kmers = (double)(mst.kmers_valid + mst.kmers_invalid);
-		printf("GPU mapping: %.3f s wall (parse + H2D + kernels), %.3e read k-mers/s end to end; index build %.3f s\n", t_map1 - t_map0,
-		    kmers / std::max(1e-9, t_map1 - t_map0), t_index1 - t_index0);
+		printf("GPU mapping: %.3f s wall (parse + H2D + kernels), %.3e read k-mers/s end to end; index build %.3f s; %zu blocks parsed in "
+		       "parallel\n",
+		    t_map1 - t_map0, kmers / std::max(1e-9, t_map1 - t_map0), t_index1 - t_index0, fast_blocks);
 	}
 
 	// ---- pairContigs (Arcs.cpp:1378-1435) on the GPU

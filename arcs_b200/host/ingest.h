@@ -1,0 +1,664 @@
+// ingest.h -- read-pair ingest of the `arcs --arks` drop-in: chromiumRead's record loop
+// (Arcs/Arcs.cpp:1185-1265) restated twice over the same sink:
+//
+//  * ingest_sequential: record by record through SeqReader (the faithful reader of seq_reader.h);
+//    handles everything the reference's reader handles (FASTA, multi-line records, CRLF, garbage
+//    between records, truncated files, NUL bytes ...).
+//  * ingest_parallel_blocks: for the shape real read files have -- strict 4-line
+//    FASTQ -- a reader thread cuts the (plain or gzip) byte stream into blocks of whole read pairs,
+//    worker threads parse blocks straight into pinned batch buffers (names, BX barcodes, pairing rule,
+//    block-local barcode interning), and the caller's thread commits blocks in file order (global
+//    barcode ids, multiplicities, submission to the GPU).  Every block is checked for strictness
+//    while it is parsed; at the first block that is not strict (and for the last few lines of every
+//    file) the remaining bytes go through ingest_sequential, so results never depend on which path
+//    ran.  tests/test_host_cpu.py compares the two paths record for record.
+#pragma once
+#include "seq_reader.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <fcntl.h>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unistd.h>
+#include <unordered_map>
+#include <vector>
+
+namespace arks_host {
+
+// ---- barcodes (ids by first appearance; indexMultMap of the reference) -------------------------
+struct Barcodes
+{
+	std::unordered_map<std::string, uint32_t> id;
+	std::vector<std::string> name;
+	std::vector<int32_t> mult;    // indexMultMap value
+	std::vector<uint8_t> counted; // the barcode is a key of indexMultMap
+	uint32_t intern(const std::string& b)
+	{
+		auto it = id.find(b);
+		if (it != id.end())
+			return it->second;
+		uint32_t i = (uint32_t)name.size();
+		id.emplace(b, i);
+		name.push_back(b);
+		mult.push_back(0);
+		counted.push_back(0);
+		return i;
+	}
+};
+
+// stripReadNum (Arcs.cpp:243-254): returns the length of the name without its read number
+inline size_t stripped_length(const char* name, size_t n)
+{
+	size_t pos = n;
+	while (pos > 0 && name[pos - 1] != '/')
+		--pos;
+	if (pos == 0) // no '/'
+		return n;
+	pos -= 1; // index of the last '/'
+	if (pos == 0 || pos == n - 1)
+		return n;
+	if (!std::isdigit((unsigned char)name[pos + 1]))
+		return n;
+	return pos;
+}
+
+inline void strip_read_num(std::string& name)
+{
+	name.resize(stripped_length(name.data(), name.size()));
+}
+
+// barcode = text after the first "BX:Z:" up to the next ' ' (Arcs.cpp:1227-1251); false if there is no tag
+inline bool find_bx(const char* c, size_t n, const char** b, size_t* bn)
+{
+	static const char tag[] = "BX:Z:";
+	const char* end = c + n;
+	const char* t = std::search(c, end, tag, tag + 5);
+	if (t == end)
+		return false;
+	const char* sp = (const char*)memchr(t, ' ', (size_t)(end - t));
+	*b = t + 5;
+	*bn = (size_t)((sp ? sp : end) - (t + 5));
+	return true;
+}
+
+inline void extract_bx(const std::string& comment, std::string& barcode)
+{
+	const char* b;
+	size_t bn;
+	if (find_bx(comment.data(), comment.size(), &b, &bn))
+		barcode.assign(b, bn);
+	else
+		barcode.clear();
+}
+
+// readBarcodes' counting rule for one record (Arcs.cpp:514-537)
+inline void count_barcode(const SeqRecord& r, Barcodes& bc, std::string& scratch)
+{
+	if (r.comment.empty())
+		return;
+	if (r.comment.find("BX:Z:") == std::string::npos)
+		return;
+	extract_bx(r.comment, scratch);
+	uint32_t i = bc.intern(scratch);
+	bc.mult[i]++;
+	bc.counted[i] = 1;
+}
+
+struct IngestCounters
+{
+	size_t skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0, count = 0;
+};
+
+struct IngestConfig
+{
+	bool mult_known = false; // multiplicities came from -u or a first pass: unknown barcodes are rejected
+	bool verbose = false;
+	int min_mult = 0, max_mult = 0;
+};
+
+// one parsed block of read pairs in caller-provided (pinned) buffers
+struct PairBatch
+{
+	char* bases = nullptr;
+	uint32_t* off = nullptr; // 2 n_pairs + 1 offsets into bases
+	uint32_t* bc = nullptr;  // barcode id per pair
+	uint64_t cap_bases = 0;
+	uint32_t cap_pairs = 0;
+	uint64_t n_bases = 0;
+	uint32_t n_pairs = 0;
+};
+
+struct PairSink
+{
+	// one accepted pair (sequential path)
+	std::function<void(const std::string& s1, const std::string& s2, uint32_t barcode)> add;
+	// a whole block of accepted pairs (parallel path); the buffers may be reused when it returns
+	std::function<void(const PairBatch& b)> submit;
+};
+
+// ---- the faithful record loop ---------------------------------------------------------------
+// `counting`: readBarcodes' multiplicity count is still running for this file (it stops at the first
+// record with an empty sequence, Arcs.cpp:516/538-540)
+inline void ingest_sequential(SeqReader& rd, Barcodes& bc, const IngestConfig& cfg, bool& counting, IngestCounters& ctr, PairSink& sink)
+{
+	SeqRecord r1, r2;
+	std::string b1, b2, n1, n2, scratch;
+	bool stop = false;
+	while (!stop) {
+		bool paired = false;
+		r1.name.clear();
+		r2.name.clear();
+		r1.comment.clear();
+		r2.comment.clear();
+		int l = rd.read(r1);
+		if (l >= 0) {
+			r1.truncate_at_nul();
+			if (counting) {
+				if (l > 0)
+					count_barcode(r1, bc, scratch);
+				else
+					counting = false;
+			}
+			l = rd.read(r2);
+			if (l >= 0) {
+				r2.truncate_at_nul();
+				if (counting) {
+					if (l > 0)
+						count_barcode(r2, bc, scratch);
+					else
+						counting = false;
+				}
+			} else {
+				r2.name.clear();
+				r2.comment.clear();
+				stop = true;
+			}
+		} else {
+			stop = true;
+		}
+		n1 = r1.name;
+		n2 = stop && l < 0 && r2.name.empty() ? std::string() : r2.name;
+		strip_read_num(n1);
+		strip_read_num(n2);
+		if (n1 == n2) {
+			paired = true;
+		} else {
+			std::cout << "File contains unpaired reads: " << n1 << " " << n2 << std::endl;
+			ctr.skipped_unpaired++;
+		}
+		ctr.count += 2;
+		if (cfg.verbose && ctr.count % 10000000 == 0)
+			std::cout << "Processed " << ctr.count << " read pairs." << std::endl;
+		if (stop)
+			break;
+		extract_bx(r1.comment, b1);
+		extract_bx(r2.comment, b2);
+		if (b1.empty() || b2.empty()) {
+			ctr.emptybarcode++;
+			continue;
+		}
+		if (!paired || b1 != b2) {
+			// (the reference still looks barcode1 up here, only to count invalid barcodes)
+			continue;
+		}
+		uint32_t id;
+		if (cfg.mult_known) {
+			auto it = bc.id.find(b1);
+			if (it == bc.id.end() || !bc.counted[it->second]) {
+				ctr.invalidbarcode++;
+				continue;
+			}
+			id = it->second;
+			const int m = bc.mult[id];
+			if (!(m > cfg.min_mult || m < cfg.max_mult)) { // goodmult, Arcs.cpp:1267
+				ctr.skipped_badmult++;
+				continue;
+			}
+		} else {
+			id = bc.intern(b1); // validity (is it a key of indexMultMap) is settled after the pass
+		}
+		sink.add(r1.seq, r2.seq, id);
+	}
+}
+
+// ---- strict 4-line FASTQ blocks ------------------------------------------------------------------
+struct Block
+{
+	uint64_t seq = 0;
+	const char* data = nullptr; // whole read pairs: a multiple of 8 lines, ends with '\n'
+	size_t size = 0;
+	int slot = -1;
+	PairBatch out; // filled by parse_block (bc = block-local ids unless cfg.mult_known)
+	bool regular = false;
+	std::vector<std::string> local_barcodes; // block-local barcode table ...
+	std::vector<int32_t> local_counts;       // ... and the number of records carrying each (readBarcodes' count)
+	size_t records = 0, skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0;
+	std::string messages;
+};
+
+// Parses one block.  Returns false (block.regular = false) at the first thing that is not a strict
+// 4-line FASTQ record as the reference's reader would see it: '@' header, one non-empty sequence
+// line that does not start with '@', '>' or '+', a '+' line, a quality line of the same length;
+// no CR, no NUL.  `frozen` (only with cfg.mult_known) is read concurrently and must not change.
+inline bool parse_block(Block& b, const IngestConfig& cfg, const Barcodes* frozen)
+{
+	b.regular = false;
+	b.out.n_pairs = 0;
+	b.out.n_bases = 0;
+	const char* p = b.data;
+	const size_t size = b.size;
+	const char* const end = p + size;
+	if (size == 0 || end[-1] != '\n' || memchr(p, 0, size) || memchr(p, '\r', size))
+		return false;
+	std::unordered_map<std::string, uint32_t> local;
+	std::string last_key;
+	uint32_t last_id = UINT32_MAX;
+	std::string key;
+	auto intern_local = [&](const char* s, size_t n) -> uint32_t {
+		if (last_id != UINT32_MAX && last_key.size() == n && memcmp(last_key.data(), s, n) == 0)
+			return last_id;
+		key.assign(s, n);
+		auto it = local.find(key);
+		uint32_t id;
+		if (it != local.end()) {
+			id = it->second;
+		} else {
+			id = (uint32_t)b.local_barcodes.size();
+			local.emplace(key, id);
+			b.local_barcodes.push_back(key);
+			b.local_counts.push_back(0);
+		}
+		last_key = key;
+		last_id = id;
+		return id;
+	};
+	struct Rec
+	{
+		const char *name, *comment, *seq;
+		size_t name_n, comment_n, seq_n;
+	};
+	while (p < end) {
+		Rec r[2];
+		for (int m = 0; m < 2; ++m) {
+			if (p >= end || *p != '@')
+				return false;
+			const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+			if (!nl)
+				return false;
+			const char* h = p + 1;
+			const char* q = h;
+			while (q < nl && !isspace((unsigned char)*q))
+				++q;
+			r[m].name = h;
+			r[m].name_n = (size_t)(q - h);
+			r[m].comment = q < nl ? q + 1 : nl;
+			r[m].comment_n = (size_t)(nl - r[m].comment);
+			const char* s = nl + 1;
+			const char* nl2 = s < end ? (const char*)memchr(s, '\n', (size_t)(end - s)) : nullptr;
+			if (!nl2 || nl2 == s || *s == '@' || *s == '>' || *s == '+')
+				return false;
+			r[m].seq = s;
+			r[m].seq_n = (size_t)(nl2 - s);
+			const char* pl = nl2 + 1;
+			if (pl >= end || *pl != '+')
+				return false;
+			const char* nl3 = (const char*)memchr(pl, '\n', (size_t)(end - pl));
+			if (!nl3)
+				return false;
+			const char* ql = nl3 + 1;
+			if ((size_t)(end - ql) < r[m].seq_n + 1 || ql[r[m].seq_n] != '\n')
+				return false;
+			if (memchr(ql, '\n', r[m].seq_n)) // quality shorter than the sequence: the reader would go on to the next line
+				return false;
+			p = ql + r[m].seq_n + 1;
+			b.records++;
+		}
+		// readBarcodes' count (every record whose comment has a BX tag), then chromiumRead's pair rule
+		const char* bx[2] = { nullptr, nullptr };
+		size_t bxn[2] = { 0, 0 };
+		uint32_t lid[2] = { 0, 0 };
+		for (int m = 0; m < 2; ++m)
+			if (r[m].comment_n && find_bx(r[m].comment, r[m].comment_n, &bx[m], &bxn[m])) {
+				if (!cfg.mult_known) {
+					lid[m] = intern_local(bx[m], bxn[m]);
+					b.local_counts[lid[m]]++;
+				}
+			} else {
+				bx[m] = nullptr;
+				bxn[m] = 0;
+			}
+		const size_t n1 = stripped_length(r[0].name, r[0].name_n), n2 = stripped_length(r[1].name, r[1].name_n);
+		const bool paired = n1 == n2 && memcmp(r[0].name, r[1].name, n1) == 0;
+		if (!paired) {
+			b.messages.append("File contains unpaired reads: ").append(r[0].name, n1).append(" ").append(r[1].name, n2).append("\n");
+			b.skipped_unpaired++;
+		}
+		if (bxn[0] == 0 || bxn[1] == 0) {
+			b.emptybarcode++;
+			continue;
+		}
+		if (!paired || bxn[0] != bxn[1] || memcmp(bx[0], bx[1], bxn[0]) != 0)
+			continue;
+		uint32_t id;
+		if (cfg.mult_known) {
+			key.assign(bx[0], bxn[0]);
+			auto it = frozen->id.find(key);
+			if (it == frozen->id.end() || !frozen->counted[it->second]) {
+				b.invalidbarcode++;
+				continue;
+			}
+			id = it->second;
+			const int mlt = frozen->mult[id];
+			if (!(mlt > cfg.min_mult || mlt < cfg.max_mult)) {
+				b.skipped_badmult++;
+				continue;
+			}
+		} else {
+			id = lid[0];
+		}
+		PairBatch& o = b.out;
+		if (o.n_pairs >= o.cap_pairs || o.n_bases + r[0].seq_n + r[1].seq_n > o.cap_bases || o.n_bases + r[0].seq_n + r[1].seq_n > 0xFFFFFFF0ull)
+			return false; // cannot happen for blocks cut by the reader; be safe
+		o.off[2 * o.n_pairs] = (uint32_t)o.n_bases;
+		memcpy(o.bases + o.n_bases, r[0].seq, r[0].seq_n);
+		o.n_bases += r[0].seq_n;
+		o.off[2 * o.n_pairs + 1] = (uint32_t)o.n_bases;
+		memcpy(o.bases + o.n_bases, r[1].seq, r[1].seq_n);
+		o.n_bases += r[1].seq_n;
+		o.bc[o.n_pairs] = id;
+		o.n_pairs++;
+	}
+	b.out.off[2 * b.out.n_pairs] = (uint32_t)b.out.n_bases;
+	b.regular = true;
+	return true;
+}
+
+// number of '\n' bytes in [p, p + n)
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) inline size_t count_newlines_avx2(const char* p, size_t n)
+{
+	const __m256i nl = _mm256_set1_epi8('\n');
+	size_t c = 0, i = 0;
+	for (; i + 32 <= n; i += 32)
+		c += (size_t)__builtin_popcount((unsigned)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), nl)));
+	for (; i < n; ++i)
+		c += p[i] == '\n';
+	return c;
+}
+#endif
+inline size_t count_newlines(const char* p, size_t n)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+	static const bool have_avx2 = __builtin_cpu_supports("avx2");
+	if (have_avx2)
+		return count_newlines_avx2(p, n);
+#endif
+	size_t c = 0;
+	for (size_t i = 0; i < n; ++i)
+		c += p[i] == '\n';
+	return c;
+}
+
+// ---- the block pipeline --------------------------------------------------------------------------
+struct ParallelIngestOptions
+{
+	int workers = 4;
+	size_t block_bytes = 8u << 20;
+	// pinned buffers for the parsed pairs, one set per block in flight (allocated by the caller)
+	std::vector<PairBatch> slots;
+};
+
+// Reads `path` (plain or gzip) block-wise.  Regular blocks are committed in file order through
+// sink.submit (after the block-local barcode ids have been replaced by global ones); from the first
+// irregular block on, and for the tail of the file, the bytes go through ingest_sequential.
+// Returns false if the file cannot be opened.
+inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const IngestConfig& cfg, bool& counting, IngestCounters& ctr,
+    PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr)
+{
+	// plain regular files are read with read(2) straight into the block buffers; gzip files and pipes go
+	// through zlib (transparent for plain data)
+	int fd = ::open(path.c_str(), O_RDONLY);
+	if (fd < 0)
+		return false;
+	gzFile gz = nullptr;
+	{
+		unsigned char magic[2] = { 0, 0 };
+		const bool seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
+		const bool plain = seekable && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b);
+		if (!plain) {
+			gz = gzdopen(fd, "r");
+			if (!gz) {
+				::close(fd);
+				return false;
+			}
+			gzbuffer(gz, 1u << 20);
+		}
+	}
+	auto read_some = [&](char* dst, size_t n) -> long {
+		if (gz)
+			return gzread(gz, dst, (unsigned)std::min<size_t>(n, 1u << 30));
+		long r;
+		do
+			r = ::read(fd, dst, n);
+		while (r < 0 && errno == EINTR);
+		return r;
+	};
+
+	const size_t n_slots = opt.slots.size();
+	std::vector<std::vector<char>> bufs(n_slots);
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<std::unique_ptr<Block>> todo;           // cut, waiting for a worker
+	std::map<uint64_t, std::unique_ptr<Block>> parsed;  // parsed, waiting for their turn
+	std::vector<int> free_slots;
+	for (size_t i = 0; i < n_slots; ++i)
+		free_slots.push_back((int)i);
+	bool reader_done = false, stop = false;
+	std::string tail; // bytes after the last block the reader cut
+	uint64_t n_cut = 0;
+
+	// reader: cuts blocks of whole pairs = multiples of 8 lines (only meaningful for strict files;
+	// anything else is caught by parse_block and sent down the sequential path)
+	std::thread reader([&] {
+		std::string carry;
+		uint64_t seqno = 0;
+		bool eof = false;
+		while (!eof) {
+			int slot;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return stop || !free_slots.empty(); });
+				if (stop)
+					break;
+				slot = free_slots.back();
+				free_slots.pop_back();
+			}
+			std::vector<char>& buf = bufs[(size_t)slot];
+			if (buf.size() < carry.size() + opt.block_bytes)
+				buf.resize(carry.size() + opt.block_bytes);
+			memcpy(buf.data(), carry.data(), carry.size());
+			size_t have = carry.size();
+			const size_t want = carry.size() + opt.block_bytes;
+			carry.clear();
+			while (have < want) {
+				long n = read_some(buf.data() + have, want - have);
+				if (n <= 0) {
+					eof = true;
+					break;
+				}
+				have += (size_t)n;
+			}
+			// the longest prefix made of whole groups of 8 lines: count the newlines, then step back over
+			// the ones that are too many
+			const char* base = buf.data();
+			size_t cut = 0;
+			{
+				const size_t lines = count_newlines(base, have);
+				size_t drop = lines & 7u; // newlines after the last whole group
+				const char* e = base + have;
+				if (lines >= 8) {
+					// e moves to just behind the (lines - drop)-th newline
+					const char* last = (const char*)memrchr(base, '\n', have);
+					e = last + 1;
+					while (drop--) {
+						last = (const char*)memrchr(base, '\n', (size_t)(last - base));
+						e = last + 1;
+					}
+					cut = (size_t)(e - base);
+				}
+			}
+			carry.assign(base + cut, have - cut);
+			if (cut == 0) {
+				std::lock_guard<std::mutex> lk(mu);
+				free_slots.push_back(slot);
+				if (!eof && carry.size() > 4 * opt.block_bytes) // lines longer than a block: not the strict shape
+					stop = true;
+				cv.notify_all();
+				if (stop)
+					break;
+				continue;
+			}
+			std::unique_ptr<Block> b(new Block());
+			b->seq = seqno++;
+			b->data = base;
+			b->size = cut;
+			b->slot = slot;
+			b->out = opt.slots[(size_t)slot];
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				todo.push_back(std::move(b));
+				n_cut = seqno;
+			}
+			cv.notify_all();
+		}
+		std::lock_guard<std::mutex> lk(mu);
+		tail.swap(carry);
+		reader_done = true;
+		cv.notify_all();
+	});
+
+	std::vector<std::thread> workers;
+	for (int w = 0; w < std::max(1, opt.workers); ++w)
+		workers.emplace_back([&] {
+			for (;;) {
+				std::unique_ptr<Block> b;
+				{
+					std::unique_lock<std::mutex> lk(mu);
+					cv.wait(lk, [&] { return !todo.empty() || reader_done || stop; });
+					if (todo.empty())
+						return;
+					b = std::move(todo.front());
+					todo.pop_front();
+				}
+				parse_block(*b, cfg, cfg.mult_known ? &bc : nullptr);
+				{
+					std::lock_guard<std::mutex> lk(mu);
+					parsed[b->seq] = std::move(b);
+				}
+				cv.notify_all();
+			}
+		});
+
+	// committer (this thread): blocks in file order
+	uint64_t next = 0;
+	size_t n_fast = 0;
+	std::vector<uint32_t> gid;
+	std::unique_ptr<Block> irregular;
+	for (;;) {
+		std::unique_ptr<Block> b;
+		{
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&] { return parsed.count(next) || (reader_done && next >= n_cut); });
+			if (!parsed.count(next))
+				break; // everything that was cut has been committed
+			b = std::move(parsed[next]);
+			parsed.erase(next);
+		}
+		if (!b->regular) {
+			// stop cutting; this block and everything behind it is re-read by the faithful reader
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				stop = true;
+			}
+			cv.notify_all();
+			irregular = std::move(b);
+			break;
+		}
+		// multiplicities and global barcode ids
+		if (!cfg.mult_known) {
+			gid.resize(b->local_barcodes.size());
+			for (size_t i = 0; i < gid.size(); ++i) {
+				gid[i] = bc.intern(b->local_barcodes[i]);
+				if (counting) {
+					bc.mult[gid[i]] += b->local_counts[i];
+					bc.counted[gid[i]] = 1;
+				}
+			}
+			for (uint32_t i = 0; i < b->out.n_pairs; ++i)
+				b->out.bc[i] = gid[b->out.bc[i]];
+		}
+		if (!b->messages.empty())
+			std::cout << b->messages << std::flush;
+		ctr.skipped_unpaired += b->skipped_unpaired;
+		ctr.emptybarcode += b->emptybarcode;
+		ctr.invalidbarcode += b->invalidbarcode;
+		ctr.skipped_badmult += b->skipped_badmult;
+		const size_t before = ctr.count;
+		ctr.count += b->records; // the reference adds 2 per pair of records
+		if (cfg.verbose)
+			for (size_t c = (before / 10000000 + 1) * 10000000; c <= ctr.count; c += 10000000)
+				std::cout << "Processed " << c << " read pairs." << std::endl;
+		if (b->out.n_pairs)
+			sink.submit(b->out);
+		n_fast++;
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			free_slots.push_back(b->slot);
+		}
+		cv.notify_all();
+		next++;
+	}
+	reader.join();
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		stop = true;
+	}
+	cv.notify_all();
+	for (auto& t : workers)
+		t.join();
+	// the bytes that did not go through the block path, in file order: the irregular block, the blocks that
+	// were already cut behind it, and the tail the reader holds; then whatever is still in the stream
+	std::string prefix;
+	if (irregular) {
+		std::map<uint64_t, std::unique_ptr<Block>> rest;
+		for (auto& kv : parsed)
+			rest[kv.first] = std::move(kv.second);
+		for (auto& b : todo)
+			rest[b->seq] = std::move(b);
+		prefix.assign(irregular->data, irregular->size);
+		for (auto& kv : rest)
+			prefix.append(kv.second->data, kv.second->size);
+	}
+	prefix += tail;
+	if (n_fast_blocks)
+		*n_fast_blocks = n_fast;
+	if (!gz)
+		gz = gzdopen(fd, "r"); // plain file: zlib continues transparently at the current offset
+	SeqReader rd(gz, std::move(prefix)); // takes the stream over (and closes it)
+	ingest_sequential(rd, bc, cfg, counting, ctr, sink);
+	return true;
+}
+
+} // namespace arks_host

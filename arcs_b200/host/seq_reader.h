@@ -12,6 +12,7 @@
 //
 // Works for plain and gzip input (gzread is transparent for uncompressed files).
 #pragma once
+#include <algorithm>
 #include <cctype>
 #include <cstring>
 #include <string>
@@ -46,6 +47,15 @@ class SeqReader
 		if (m_fp)
 			gzbuffer(m_fp, 1u << 18);
 	}
+	// continues an already open stream: `prefix` (bytes that were read ahead of it) comes first.
+	// Takes ownership of fp (which may be null: then only the prefix is read).
+	SeqReader(gzFile fp, std::string prefix, size_t bufsize = 1u << 20)
+	  : m_fp(fp)
+	  , m_buf(bufsize)
+	  , m_prefix(std::move(prefix))
+	  , m_opened(true)
+	{
+	}
 	~SeqReader()
 	{
 		if (m_fp)
@@ -53,7 +63,7 @@ class SeqReader
 	}
 	SeqReader(const SeqReader&) = delete;
 	SeqReader& operator=(const SeqReader&) = delete;
-	bool ok() const { return m_fp != nullptr; }
+	bool ok() const { return m_fp != nullptr || m_opened; }
 
 	// >= 0: sequence length; -1: end of file; -2: truncated / mismatched quality
 	int read(SeqRecord& r)
@@ -102,7 +112,16 @@ class SeqReader
 		if (m_eof)
 			return false;
 		m_begin = 0;
-		int n = gzread(m_fp, m_buf.data(), (unsigned)m_buf.size());
+		if (m_prefix_pos < m_prefix.size()) {
+			const size_t n = std::min(m_buf.size(), m_prefix.size() - m_prefix_pos);
+			memcpy(m_buf.data(), m_prefix.data() + m_prefix_pos, n);
+			m_prefix_pos += n;
+			m_end = n;
+			if (m_prefix_pos == m_prefix.size())
+				std::string().swap(m_prefix), m_prefix_pos = 0;
+			return true;
+		}
+		int n = m_fp ? gzread(m_fp, m_buf.data(), (unsigned)m_buf.size()) : 0;
 		m_end = n > 0 ? (size_t)n : 0;
 		if (m_end == 0) {
 			m_eof = true;
@@ -166,6 +185,9 @@ class SeqReader
 
 	gzFile m_fp = nullptr;
 	std::vector<char> m_buf;
+	std::string m_prefix;
+	size_t m_prefix_pos = 0;
+	bool m_opened = false;
 	size_t m_begin = 0, m_end = 0;
 	bool m_eof = false;
 	int m_last = 0;

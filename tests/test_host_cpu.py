@@ -150,3 +150,117 @@ def test_reader_random_text(tmp_path):
         for bufsize in (5, 1 << 16):
             out = subprocess.run([DUMP, str(path), str(bufsize)], stdout=subprocess.PIPE, check=True).stdout.decode("latin1")
             assert out.split("\n")[:-1] == model_dump(data), data
+
+
+# ---- block-parallel ingest (arcs_b200/host/ingest.h) against the faithful sequential record loop ----
+INGEST = os.path.join(ROOT, "arcs_b200", "bin", "ingest_dump")
+
+
+def _build_ingest():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "arcs_b200", "host"), "../bin/ingest_dump"])
+
+
+def _ingest(mode, path, *extra):
+    p = subprocess.run([INGEST, mode, str(path)] + [str(x) for x in extra], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    fast = int(p.stderr.decode().split("FAST_BLOCKS")[1].split()[0])
+    return p.stdout, fast
+
+
+def _strict_fastq(rng, n_pairs, barcodes=7, tweak=None):
+    recs = []
+    for i in range(n_pairs):
+        bc = "BX:Z:%s-1" % "".join("ACGT"[(int(rng.integers(0, barcodes)) >> (2 * q)) & 3] for q in range(6))
+        for m in (1, 2):
+            L = int(rng.integers(20, 160))
+            seq = "".join("ACGTNacgt"[int(x)] for x in rng.integers(0, 9, L))
+            recs.append(["r%d/%d" % (i, m), bc, seq, "I" * L])
+    if tweak:
+        tweak(recs)
+    return "".join("@%s%s\n%s\n+\n%s\n" % (n, (" " + c) if c is not None else "", s, q) for n, c, s, q in recs).encode()
+
+
+def _tweak_pairing(recs):
+    recs[4][0] = "other/1"          # unpaired names (message + counter)
+    recs[10][1] = None              # no comment
+    recs[13][1] = "RG:Z:x"          # no BX on mate 2
+    recs[16][1] = recs[16][1][:-1] + "2"  # barcodes differ
+    recs[20][1] = "XY:Z:1 " + recs[20][1] + " ZZ:i:3"
+    recs[21][1] = "XY:Z:1 " + recs[21][1] + " ZZ:i:3"
+    recs[24][1] = "BX:Z:"           # empty barcode: counted under the empty name
+    recs[25][1] = "BX:Z:"
+    recs[30][0] = recs[30][0].replace("/1", "/1x")
+    recs[32][1] = recs[32][1] + "\tQT:Z:x"  # a tab does not end the barcode
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("workers,block", [(1, 2000), (3, 1000), (4, 1 << 16), (8, 1 << 20)])
+def test_parallel_ingest_equals_sequential_on_strict_fastq(workers, block, gz, tmp_path):
+    _build_ingest()
+    rng = np.random.default_rng(workers * 1000 + block)
+    data = _strict_fastq(rng, 300, tweak=_tweak_pairing)
+    path = tmp_path / ("r.fq.gz" if gz else "r.fq")
+    if gz:
+        with gzip.open(path, "wb") as f:
+            f.write(data)
+    else:
+        path.write_bytes(data)
+    want, _ = _ingest("seq", path)
+    got, fast = _ingest("par", path, workers, block)
+    assert got == want
+    assert b"File contains unpaired reads: other r2" in got
+    if block < len(data):
+        assert fast > 0  # the block path did run
+
+
+# base = strict text, c = offset of a record-pair boundary in it
+IRREGULAR = {
+    "crlf_in_the_middle": lambda d, c: d[:c] + d[c:].replace(b"\n", b"\r\n", 8),
+    "multiline_record": lambda d, c: d[:c] + b"@ml/1 BX:Z:AAAAAA-1\nACGT\nACGT\n+\nIIII\nIIII\n@ml/2 BX:Z:AAAAAA-1\nACGTACGT\n+\nIIIIIIII\n" + d[c:],
+    "fasta_record_inside": lambda d, c: d[:c] + b">f1 BX:Z:AAAAAA-1\nACGTACGT\n>f2 BX:Z:AAAAAA-1\nACGTACGT\n" + d[c:],
+    "nul_byte": lambda d, c: d[:c] + d[c:].replace(b"A", b"\0", 1),
+    "empty_sequence": lambda d, c: d[:c] + b"@e/1 BX:Z:AAAAAA-1\n\n+\n\n@e/2 BX:Z:AAAAAA-1\n\n+\n\n" + d[c:],
+    "odd_record_count": lambda d, c: d + b"@tail/1 BX:Z:AAAAAA-1\nACGT\n+\nIIII\n",
+    "no_final_newline": lambda d, c: d[:-1],
+    "truncated_quality": lambda d, c: d[:-30],
+    "junk_between_records": lambda d, c: d[:c] + b"garbage line\n\n" + d[c:],
+    "quality_longer_than_sequence": lambda d, c: d[:c] + b"@q/1 BX:Z:AAAAAA-1\nACGT\n+\nIIIIII\n" + d[c:],
+    "one_extra_record": lambda d, c: d[:c] + b"@x/1 BX:Z:AAAAAA-1\nACGT\n+\nIIII\n" + d[c:],
+    "not_fastq_at_all": lambda d, c: b">c1\nACGT\n>c2\nGGTA\n" * 50,
+    "empty_file": lambda d, c: b"",
+}
+
+
+@pytest.mark.parametrize("name", sorted(IRREGULAR))
+@pytest.mark.parametrize("workers,block", [(2, 1500), (4, 4096)])
+def test_parallel_ingest_falls_back_to_the_faithful_reader(name, workers, block, tmp_path):
+    """wherever the input stops being strict 4-line FASTQ the rest goes through the sequential reader: same
+    pairs, counters, messages and multiplicities (incl. readBarcodes' stop at the first empty sequence)"""
+    _build_ingest()
+    rng = np.random.default_rng(5)
+    base = _strict_fastq(rng, 60)
+    lines = base.split(b"\n")
+    n = base[:len(base) // 2].count(b"\n") // 8 * 8
+    cut = len(b"\n".join(lines[:n])) + 1
+    assert base[cut:cut + 1] == b"@" and base[cut - 1:cut] == b"\n"
+    data = IRREGULAR[name](base, cut)
+    path = tmp_path / "r.fq"
+    path.write_bytes(data)
+    want, _ = _ingest("seq", path)
+    got, _ = _ingest("par", path, workers, block)
+    assert got == want
+
+
+def test_parallel_ingest_with_known_multiplicities(tmp_path):
+    """-u: barcodes missing from the multiplicity file are rejected inside the block parser"""
+    _build_ingest()
+    rng = np.random.default_rng(9)
+    data = _strict_fastq(rng, 400, barcodes=12)
+    path = tmp_path / "r.fq"
+    path.write_bytes(data)
+    seen = sorted({ln.split(b"BX:Z:")[1] for ln in data.split(b"\n") if ln.startswith(b"@")})
+    mult = tmp_path / "m.csv"
+    mult.write_text("".join("%s,%d\n" % (b.decode(), 60 + i if i % 4 else 3) for i, b in enumerate(seen) if i % 3))
+    want, _ = _ingest("seq", path, 0, 0, mult)
+    got, fast = _ingest("par", path, 3, 2000, mult)
+    assert got == want and fast > 0
+    assert b"invalidbarcode=0" not in got.split(b"COUNTERS")[1].split(b"\n")[0]

@@ -57,3 +57,7 @@ if ! skip ncu; then
     python bench.py --pairs 3125000 --steps 1 --warmup 1 --no-cpu --no-e2e > $O.ncu_full.log 2>&1
 fi
 ls gpurun_out | tr '\n' ' '
+if [ -n "$WALLCLOCK" ]; then
+  timeout 900 python tools/wallclock.py --genome ${WALL_GENOME:-10000000} --pairs ${WALL_PAIRS:-2000000} > $O.wallclock.json 2> $O.wallclock.err
+  cat $O.wallclock.json
+fi
