@@ -341,10 +341,36 @@ void flush_batch(Gpu& g)
 	g.batch[g.cur].n_bases = 0;
 }
 
+// the two large pinned batches of the record-by-record path, allocated on first use (input that goes
+// through the block path never needs them, and pinning 0.5 GB takes a noticeable fraction of a second)
+void ensure_batches(Gpu& g)
+{
+	if (g.batch[0].bases)
+		return;
+	for (auto& b : g.batch) {
+		void* p;
+		if (arks_host_alloc(&p, kBatchBases + 64) != ARKS_OK)
+			die("error: cannot allocate pinned host memory");
+		b.bases = (char*)p;
+		if (arks_host_alloc(&p, (2ull * kBatchPairs + 1) * 4) != ARKS_OK)
+			die("error: cannot allocate pinned host memory");
+		b.off = (uint32_t*)p;
+		if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
+			die("error: cannot allocate pinned host memory");
+		b.bc = (uint32_t*)p;
+		if (params.dist_est) {
+			if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
+				die("error: cannot allocate pinned host memory");
+			b.out = (int32_t*)p;
+		}
+	}
+}
+
 void add_pair(Gpu& g, const char* s1, size_t l1, const char* s2, size_t l2, uint32_t barcode)
 {
 	if (l1 + l2 > kBatchBases / 2)
 		die("error: read pair longer than the batch buffer");
+	ensure_batches(g);
 	Gpu::Batch* b = &g.batch[g.cur];
 	if (b->n_pairs >= kBatchPairs || b->n_bases + l1 + l2 > kBatchBases) {
 		flush_batch(g);
@@ -874,23 +900,6 @@ int main(int argc, char** argv)
 		}
 		if (any)
 			ck(g.h, arks_set_conreci_remap(g.h, remap.data(), (uint32_t)remap.size()), "arks_set_conreci_remap");
-		for (auto& b : g.batch) {
-			void* p;
-			if (arks_host_alloc(&p, kBatchBases + 64) != ARKS_OK)
-				die("error: cannot allocate pinned host memory");
-			b.bases = (char*)p;
-			if (arks_host_alloc(&p, (2ull * kBatchPairs + 1) * 4) != ARKS_OK)
-				die("error: cannot allocate pinned host memory");
-			b.off = (uint32_t*)p;
-			if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
-				die("error: cannot allocate pinned host memory");
-			b.bc = (uint32_t*)p;
-			if (params.dist_est) {
-				if (arks_host_alloc(&p, kBatchPairs * 4ull) != ARKS_OK)
-					die("error: cannot allocate pinned host memory");
-				b.out = (int32_t*)p;
-			}
-		}
 	}
 	const double t_index1 = now();
 	end_bases.clear();
@@ -931,7 +940,7 @@ int main(int argc, char** argv)
 		};
 		// block-parallel parsing (ingest.h) unless -D needs the pairs' input order or ARKS_PARSE_THREADS=0
 		arks_host::ParallelIngestOptions popt;
-		popt.workers = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+		popt.workers = (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency()));
 		if (const char* e = getenv("ARKS_PARSE_THREADS"))
 			popt.workers = atoi(e);
 		if (const char* e = getenv("ARKS_PARSE_BLOCK_MB"))
@@ -1345,6 +1354,8 @@ int main(int argc, char** argv)
 		    t_map1 - t_map0);
 	for (auto& gp : gpus) {
 		for (auto& b : gp.batch) {
+			if (!b.bases)
+				continue;
 			arks_host_free(b.bases);
 			arks_host_free(b.off);
 			arks_host_free(b.bc);

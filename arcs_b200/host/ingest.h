@@ -29,6 +29,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
 #include <unordered_map>
@@ -415,7 +417,7 @@ inline size_t count_newlines(const char* p, size_t n)
 struct ParallelIngestOptions
 {
 	int workers = 4;
-	size_t block_bytes = 8u << 20;
+	size_t block_bytes = 4u << 20;
 	// pinned buffers for the parsed pairs, one set per block in flight (allocated by the caller)
 	std::vector<PairBatch> slots;
 };
@@ -427,17 +429,28 @@ struct ParallelIngestOptions
 inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const IngestConfig& cfg, bool& counting, IngestCounters& ctr,
     PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr)
 {
-	// plain regular files are read with read(2) straight into the block buffers; gzip files and pipes go
-	// through zlib (transparent for plain data)
+	// plain regular files are memory-mapped (blocks are cut in place, nothing is copied); gzip files and
+	// pipes go through zlib (transparent for plain data) into block buffers
 	int fd = ::open(path.c_str(), O_RDONLY);
 	if (fd < 0)
 		return false;
 	gzFile gz = nullptr;
+	const char* map = nullptr;
+	size_t map_size = 0;
 	{
 		unsigned char magic[2] = { 0, 0 };
-		const bool seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
-		const bool plain = seekable && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b);
-		if (!plain) {
+		struct stat st;
+		const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
+		const bool plain = regular && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b);
+		if (plain) {
+			void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (m != MAP_FAILED) {
+				map = (const char*)m;
+				map_size = (size_t)st.st_size;
+				madvise(m, map_size, MADV_SEQUENTIAL);
+			}
+		}
+		if (!map) {
 			gz = gzdopen(fd, "r");
 			if (!gz) {
 				::close(fd);
@@ -446,15 +459,8 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 			gzbuffer(gz, 1u << 20);
 		}
 	}
-	auto read_some = [&](char* dst, size_t n) -> long {
-		if (gz)
-			return gzread(gz, dst, (unsigned)std::min<size_t>(n, 1u << 30));
-		long r;
-		do
-			r = ::read(fd, dst, n);
-		while (r < 0 && errno == EINTR);
-		return r;
-	};
+	size_t map_pos = 0; // mapped files: first byte that has not been cut into a block (reader thread)
+	auto read_some = [&](char* dst, size_t n) -> long { return gzread(gz, dst, (unsigned)std::min<size_t>(n, 1u << 30)); };
 
 	const size_t n_slots = opt.slots.size();
 	std::vector<std::vector<char>> bufs(n_slots);
@@ -475,6 +481,7 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 		std::string carry;
 		uint64_t seqno = 0;
 		bool eof = false;
+		size_t span = opt.block_bytes; // mapped files: bytes looked at for the next block
 		while (!eof) {
 			int slot;
 			{
@@ -485,24 +492,32 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 				slot = free_slots.back();
 				free_slots.pop_back();
 			}
-			std::vector<char>& buf = bufs[(size_t)slot];
-			if (buf.size() < carry.size() + opt.block_bytes)
-				buf.resize(carry.size() + opt.block_bytes);
-			memcpy(buf.data(), carry.data(), carry.size());
-			size_t have = carry.size();
-			const size_t want = carry.size() + opt.block_bytes;
-			carry.clear();
-			while (have < want) {
-				long n = read_some(buf.data() + have, want - have);
-				if (n <= 0) {
-					eof = true;
-					break;
+			const char* base;
+			size_t have;
+			if (map) {
+				base = map + map_pos;
+				have = std::min(span, map_size - map_pos);
+				eof = map_pos + have == map_size;
+			} else {
+				std::vector<char>& buf = bufs[(size_t)slot];
+				if (buf.size() < carry.size() + opt.block_bytes)
+					buf.resize(carry.size() + opt.block_bytes);
+				memcpy(buf.data(), carry.data(), carry.size());
+				have = carry.size();
+				const size_t want = carry.size() + opt.block_bytes;
+				carry.clear();
+				while (have < want) {
+					long n = read_some(buf.data() + have, want - have);
+					if (n <= 0) {
+						eof = true;
+						break;
+					}
+					have += (size_t)n;
 				}
-				have += (size_t)n;
+				base = buf.data();
 			}
 			// the longest prefix made of whole groups of 8 lines: count the newlines, then step back over
 			// the ones that are too many
-			const char* base = buf.data();
 			size_t cut = 0;
 			{
 				const size_t lines = count_newlines(base, have);
@@ -519,11 +534,16 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 					cut = (size_t)(e - base);
 				}
 			}
-			carry.assign(base + cut, have - cut);
+			if (map) {
+				map_pos += cut;
+				span = cut ? opt.block_bytes : span + opt.block_bytes; // no whole pair in sight: look further
+			} else {
+				carry.assign(base + cut, have - cut);
+			}
 			if (cut == 0) {
 				std::lock_guard<std::mutex> lk(mu);
 				free_slots.push_back(slot);
-				if (!eof && carry.size() > 4 * opt.block_bytes) // lines longer than a block: not the strict shape
+				if (!eof && (map ? span : carry.size()) > 4 * opt.block_bytes) // lines longer than a block: not the strict shape
 					stop = true;
 				cv.notify_all();
 				if (stop)
@@ -654,8 +674,12 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 	prefix += tail;
 	if (n_fast_blocks)
 		*n_fast_blocks = n_fast;
-	if (!gz)
-		gz = gzdopen(fd, "r"); // plain file: zlib continues transparently at the current offset
+	if (map) {
+		// mapped file: the stream continues behind the last block that was cut (zlib reads plain data as is)
+		munmap((void*)map, map_size);
+		lseek(fd, (off_t)map_pos, SEEK_SET);
+		gz = gzdopen(fd, "r");
+	}
 	SeqReader rd(gz, std::move(prefix)); // takes the stream over (and closes it)
 	ingest_sequential(rd, bc, cfg, counting, ctr, sink);
 	return true;
