@@ -18,7 +18,8 @@
 //    and the line order of --samples_tsv); the same containers are filled in the same order here
 //    (barcodes in the order their first pair was stored, which the GPU reports per pair under -D), so
 //    the output equals the reference's at -t 1 built with the same libstdc++.
-//  * the alignment (non --arks) mode is not implemented.
+//  * the alignment mode (no --arks: SAM text in, Arcs.cpp:572-771) tallies read pairs on the host and hands
+//    the IndexMap rows to the same GPU pair-link kernel.
 #include "../../include/arks_b200.h"
 #include "ingest.h"
 #include "seq_reader.h"
@@ -403,6 +404,241 @@ struct Graph
 	std::vector<Edge> edges;      // in pmap order
 };
 
+// ---- ARCS alignment mode: readBAM (Arcs/Arcs.cpp:572-771) -----------------------------------------
+// SAM text (the pipeline feeds `samtools view -h`), read pairs on consecutive lines.  A pair whose two
+// alignments pass the flag / MAPQ / identity tests and hit the same contig is tallied under its barcode
+// at the head or the tail of that contig by the mean of the two positions -- when the NEXT read name
+// arrives (so the last pair of a file is never tallied, as upstream).  The tallies become IndexMap rows
+// for the GPU pair-link kernel (arks_imap_add).
+struct AlignRows
+{
+	std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> ht; // barcode << 32 | contig -> head, tail
+	std::vector<uint64_t> first_add;                                 // per barcode: order of its first tally
+	uint64_t n_adds = 0;
+};
+
+uint32_t intern_contig(Contigs& ct, std::unordered_map<std::string, uint32_t>& contig_id, const std::string& name, int length, bool overwrite)
+{
+	auto it = contig_id.find(name);
+	if (it != contig_id.end()) {
+		if (overwrite) {
+			ct.length[it->second] = length;
+			ct.to_length[name] = length;
+		}
+		return it->second;
+	}
+	const uint32_t i = (uint32_t)ct.name.size();
+	contig_id.emplace(name, i);
+	ct.name.push_back(name);
+	ct.length.push_back(length);
+	ct.first_of_name.push_back(i);
+	ct.to_length[name] = length;
+	return i;
+}
+
+// checkFlag (Arcs.cpp:204-211): PAIRED,PROPER_PAIR with exactly one of REVERSE / MREVERSE
+bool accepted_flag(int flag)
+{
+	flag &= ~0xc0;
+	return flag == 19 || flag == 35;
+}
+
+// calcSequenceIdentity (Arcs.cpp:275-315): aligned query length (M,=,X,I) minus NM, over the read length, in percent
+double sequence_identity(const std::string& line, const std::string& cigar, const std::string& seq)
+{
+	int qalen = 0;
+	long num = 0;
+	bool have_digits = false, broken = false;
+	for (char c : cigar) {
+		if (isdigit((unsigned char)c)) {
+			num = num * 10 + (c - '0');
+			have_digits = true;
+		} else {
+			if (c == 'M' || c == '=' || c == 'X' || c == 'I') {
+				if (!have_digits)
+					broken = true; // upstream's stream extraction fails here and stays failed
+				if (!broken)
+					qalen += (int)num;
+			}
+			num = 0;
+			have_digits = false;
+		}
+	}
+	int edit_dist = 0;
+	const size_t found = line.find("NM:i:");
+	if (found != std::string::npos)
+		edit_dist = (int)std::strtol(&line[found + 5], 0, 10);
+	double si = 0;
+	if (qalen != 0) {
+		const double mins = qalen - edit_dist;
+		si = mins / seq.length() * 100;
+	}
+	return si;
+}
+
+// parseBXTag (Common/SAM.h:9-33): first "BX:Z:" up to the next blank, tab, CR or LF
+std::string sam_bx_tag(const std::string& s)
+{
+	size_t start = s.find("BX:Z:");
+	if (start == std::string::npos)
+		return std::string();
+	start += 5;
+	size_t end = s.find_first_of(" \t\r\n", start);
+	if (end == std::string::npos)
+		end = s.length();
+	return s.substr(start, end - start);
+}
+
+void read_alignments(const std::string& path, Barcodes& bc, Contigs& ct, std::unordered_map<std::string, uint32_t>& contig_id, AlignRows& rows)
+{
+	std::ifstream in(path.c_str());
+	if (!in.good()) {
+		std::cerr << "error: `" << path << "': " << strerror(errno) << std::endl;
+		exit(EXIT_FAILURE);
+	}
+	if (in.peek() == EOF) {
+		std::cerr << "error: alignments file is empty: " << path << '\n';
+		exit(EXIT_FAILURE);
+	}
+	std::string prevRN, readyIndex, prevRef, readyRef;
+	int prevSI = 0, prevFlag = 0, prevMapq = 0, prevPos = -1, readyPos = -1;
+	int nth = 1; // which alignment of the current read name this line is
+	size_t linecount = 0, countUnpaired = 0;
+	const bool add_sq_lengths = ct.to_length.empty();
+	std::string line;
+	while (getline(in, line)) {
+		if (line.empty())
+			continue;
+		if (line[0] == '@') {
+			if (line.compare(0, 4, "@SQ\t") == 0) {
+				// "@SQ\tSN:<name>\tLN:<size>" (upstream reads it with `expect` manipulators and exits on anything else)
+				std::string name;
+				size_t size = 0;
+				bool ok = line.compare(0, 7, "@SQ\tSN:") == 0;
+				size_t p = 7;
+				if (ok) {
+					while (p < line.size() && !isspace((unsigned char)line[p]))
+						name.push_back(line[p++]);
+					ok = !name.empty() && line.compare(p, 4, "\tLN:") == 0;
+					p += 4;
+				}
+				if (ok) {
+					size_t q = p;
+					while (q < line.size() && isdigit((unsigned char)line[q]))
+						size = size * 10 + (size_t)(line[q++] - '0');
+					ok = q > p;
+				}
+				if (!ok) {
+					std::cerr << "error: parsing SAM header: " << line << '\n';
+					exit(EXIT_FAILURE);
+				}
+				if (add_sq_lengths) {
+					if (!contig_id.count(name))
+						intern_contig(ct, contig_id, name, (int)size, false);
+				} else {
+					auto it = ct.to_length.find(name);
+					if (it == ct.to_length.end()) {
+						std::cerr << "error: unexpected sequence: " << name << " of size " << size;
+						exit(EXIT_FAILURE);
+					} else if (it->second != (int)size) {
+						std::cerr << "error: mismatched sequence lengths: sequence " << name << ": " << it->second << " != " << size;
+						exit(EXIT_FAILURE);
+					}
+				}
+			}
+			continue;
+		}
+		linecount++;
+		std::stringstream ss(line);
+		std::string readName, scafName, cigar, rnext, seq, qual, tags;
+		int flag = 0, pos = 0, mapq = 0, pnext = 0, tlen = 0;
+		ss >> readName >> flag >> scafName >> pos >> mapq >> cigar >> rnext >> pnext >> tlen >> seq >> qual >> std::ws;
+		getline(ss, tags);
+		// barcode: BX tag, else the suffix of the read name after the last '_' if it is all ACGT
+		std::string index = sam_bx_tag(tags);
+		if (index.empty()) {
+			const size_t found = readName.rfind("_");
+			if (found != std::string::npos) {
+				index = readName.substr(found + 1);
+				if (index.find_first_not_of("ACGTacgt") != std::string::npos)
+					index.clear();
+			}
+		}
+		// multiplicity counts primary, non-supplementary alignments
+		if (!index.empty() && !((flag & 0x800) || (flag & 0x100))) {
+			const uint32_t b = bc.intern(index);
+			bc.mult[b]++;
+			bc.counted[b] = 1;
+		}
+		const int si = (int)sequence_identity(line, cigar, seq);
+		if (nth == 2 && readName != prevRN) {
+			if (countUnpaired == 0)
+				std::cerr << "Warning: Skipping an unpaired read. Read pairs should be consecutive in the SAM/BAM file.\n"
+				             "  Prev read: "
+				          << prevRN << "\n  Curr read: " << readName << std::endl;
+			++countUnpaired;
+			if (countUnpaired % 1000000 == 0)
+				std::cerr << "Warning: Skipped " << countUnpaired << " unpaired reads." << std::endl;
+			nth = 1;
+		}
+		if (nth >= 3)
+			nth = 1;
+		if (nth == 1) {
+			if (readName != prevRN) {
+				prevRN = readName;
+				prevSI = si;
+				prevFlag = flag;
+				prevMapq = mapq;
+				prevRef = scafName;
+				prevPos = pos;
+				// the previous read name had exactly two alignments: tally its pair now
+				if (!readyIndex.empty() && !readyRef.empty() && readyRef != "*" && readyPos != -1) {
+					// (upstream's operator[] creates a zero-length entry for a contig it has never seen)
+					const uint32_t c = intern_contig(ct, contig_id, readyRef, 0, false);
+					const int size = ct.to_length[readyRef];
+					if (size >= params.min_size) {
+						int cutOff = params.end_length;
+						if (cutOff == 0 || size <= cutOff * 2)
+							cutOff = size / 2;
+						const bool head = readyPos <= cutOff, tail = !head && readyPos > size - cutOff;
+						if (head || tail) {
+							const uint32_t b = bc.intern(readyIndex);
+							auto& ht = rows.ht[((uint64_t)b << 32) | c];
+							(head ? ht.first : ht.second)++;
+							if (b >= rows.first_add.size())
+								rows.first_add.resize((size_t)b + 1 + rows.first_add.size() / 2, UINT64_MAX);
+							rows.first_add[b] = std::min(rows.first_add[b], rows.n_adds);
+							rows.n_adds++;
+						}
+					}
+					readyIndex.clear();
+					readyRef.clear();
+					readyPos = -1;
+				}
+			} else { // a third alignment under the same name: the name is dropped
+				nth = 0;
+				readyIndex.clear();
+				readyRef.clear();
+				readyPos = -1;
+			}
+		} else if (nth == 2) {
+			if (!seq.empty() && accepted_flag(flag) && accepted_flag(prevFlag) && mapq != 0 && prevMapq != 0 && si >= params.seq_id &&
+			    prevSI >= params.seq_id) {
+				if (prevRef == scafName && scafName != "*" && !scafName.empty() && !index.empty()) {
+					readyIndex = index;
+					readyRef = scafName;
+					readyPos = (prevPos + pos) / 2;
+				}
+			}
+		}
+		nth++;
+		if (params.verbose && linecount % 10000000 == 0)
+			std::cout << "On line " << linecount << std::endl;
+	}
+	if (countUnpaired > 0)
+		std::cerr << "Warning: Skipped " << countUnpaired << " unpaired reads. Read pairs should be consecutive in the SAM/BAM file.\n";
+}
+
 // ---- -D: distance estimation (Arcs/DistanceEst.h) over the exported IndexMap rows ----------------
 struct DistSample // DistanceEst.h:37-53
 {
@@ -753,11 +989,8 @@ int main(int argc, char** argv)
 		             "file for ARKS (--arks)). Exiting... \n";
 		dieflag = true;
 	}
-	if (!params.arks) {
-		std::cerr << PROGRAM ": error: this build implements the k-mer method only: pass --arks (alignment mode is not "
-		                     "part of the B200 hot path).\n";
-		dieflag = true;
-	}
+	if (!params.arks)
+		params.gpus = 1; // alignment mode: the tallies are made on the host; one GPU pairs them
 	{
 		std::ifstream g(params.file.c_str());
 		if (!g.good() && params.arks) {
@@ -765,16 +998,22 @@ int main(int argc, char** argv)
 			dieflag = true;
 		}
 	}
-	if (params.k_value < ARKS_MIN_K || params.k_value > ARKS_MAX_K) {
+	if (params.arks && (params.k_value < ARKS_MIN_K || params.k_value > ARKS_MAX_K)) {
 		std::cerr << PROGRAM ": error: -k must be in [" << ARKS_MIN_K << ", " << ARKS_MAX_K << "] in this build.\n";
 		dieflag = true;
 	}
-	if (params.base_name.empty()) {
+	if (params.base_name.empty()) { // Arcs.cpp:2139-2166
 		std::ostringstream fn;
-		fn << params.file << ".scaff"
-		   << "_arks"
-		   << "_c" << params.min_reads << "_k" << params.k_value << "_j" << params.j_index << "_l" << params.min_links << "_d"
-		   << params.max_degree << "_e" << params.end_length << "_r" << params.error_percent;
+		if (params.arks)
+			fn << params.file << ".scaff"
+			   << "_arks"
+			   << "_c" << params.min_reads << "_k" << params.k_value << "_j" << params.j_index << "_l" << params.min_links << "_d"
+			   << params.max_degree << "_e" << params.end_length << "_r" << params.error_percent;
+		else
+			fn << params.file << ".scaff"
+			   << "_arcs"
+			   << "_s" << params.seq_id << "_c" << params.min_reads << "_l" << params.min_links << "_d" << params.max_degree << "_e"
+			   << params.end_length << "_r" << params.error_percent;
 		params.base_name = fn.str();
 	}
 	if (params.dist_graph_name.empty())
@@ -790,7 +1029,7 @@ int main(int argc, char** argv)
 	printf("%s\n", "Finished reading user inputs...entering runArcs()...");
 
 	// ---- runArcs banner (Arcs.cpp:1818-1843)
-	std::cout << "Running: " << PROGRAM << " " << PACKAGE_VERSION << "\nARKS method\n pid " << ::getpid() << "\n -c "
+	std::cout << "Running: " << PROGRAM << " " << PACKAGE_VERSION << (params.arks ? "\nARKS" : "\nARCS") << " method\n pid " << ::getpid() << "\n -c "
 	          << params.min_reads << "\n -d " << params.max_degree << "\n -e " << params.end_length << "\n -l " << params.min_links
 	          << "\n -m " << params.min_mult << '-' << params.max_mult << "\n -r " << params.error_percent << "\n -v "
 	          << params.verbose << "\n -z " << params.min_size << "\n --gap=" << params.gap << "\n -k " << params.k_value << "\n -j "
@@ -803,8 +1042,56 @@ int main(int argc, char** argv)
 	std::cout.flush();
 	const double t_start = now();
 
-	// ---- barcode multiplicities
 	Barcodes bc;
+	Contigs ct;
+	std::vector<Gpu> gpus(params.gpus);
+	double t_index0 = now(), t_index1 = t_index0, t_map0 = t_index0, t_map1 = t_index0, t_gpu_init = 0;
+	if (!params.arks) {
+		// ---- ARCS alignment mode (runArcs :1859-1871): contig sizes from -f (getScaffSizes :549-568) and/or
+		// the SAM headers, tallies from the alignments, then the same pair-link / graph path as ARKS
+		std::unordered_map<std::string, uint32_t> contig_id;
+		if (!params.file.empty()) {
+			std::cout << "\n=> Getting scaffold sizes... " << stamp();
+			SeqReader rd(params.file);
+			if (!rd.ok())
+				die("error: cannot open " + params.file);
+			SeqRecord r;
+			int counter = 0;
+			while (rd.read(r) >= 0) {
+				r.truncate_at_nul();
+				counter++;
+				intern_contig(ct, contig_id, r.name, (int)r.seq.size(), true);
+			}
+			if (params.verbose)
+				std::cout << "Saw " << counter << " sequences.\n";
+		}
+		std::cout << "\n=> Reading alignment files... " << stamp();
+		t_map0 = now();
+		AlignRows rows;
+		for (const auto& f : filenames) {
+			if (params.verbose)
+				std::cout << "Reading alignments: " << f << std::endl;
+			read_alignments(f, bc, ct, contig_id, rows);
+		}
+		g_first_stored = rows.first_add;
+		Gpu& g = gpus[0];
+		if (arks_create(0, 32, 1024, &g.h) != ARKS_OK)
+			die(std::string("error: cannot initialise GPU 0: ") + arks_last_error(nullptr));
+		std::vector<uint32_t> rb, rc, rh, rt;
+		for (const auto& kv : rows.ht) {
+			rb.push_back((uint32_t)(kv.first >> 32));
+			rc.push_back((uint32_t)kv.first);
+			rh.push_back(kv.second.first);
+			rt.push_back(kv.second.second);
+			// pairContigs looks the multiplicity up with operator[] (Arcs.cpp:1389): a barcode that was only
+			// ever seen on secondary / supplementary alignments becomes a key with multiplicity 0
+			bc.counted[rb.back()] = 1;
+		}
+		if (!rb.empty())
+			ck(g.h, arks_imap_add(g.h, rb.data(), rc.data(), rh.data(), rt.data(), rb.size()), "arks_imap_add");
+		t_map1 = now();
+	} else {
+	// ---- barcode multiplicities
 	const bool have_multfile = !params.multfile.empty();
 	// `goodmult = mult > min || mult < max` (Arcs.cpp:1267) can only be false for an inverted range
 	const bool need_first_pass = !have_multfile && (params.two_pass || params.min_mult >= params.max_mult);
@@ -835,7 +1122,6 @@ int main(int argc, char** argv)
 
 	// ---- contigs: getContigKmers (Arcs.cpp:1021-1129) on the GPU
 	std::cout << "\n=>Preprocessing: Gathering draft information..." << stamp() << "\n";
-	Contigs ct;
 	std::vector<char> end_bases;
 	std::vector<uint64_t> end_off(1, 0);
 	std::vector<uint32_t> end_conreci;
@@ -876,14 +1162,15 @@ int main(int argc, char** argv)
 		std::cerr << "Number of contigs:" << ct.name.size() << "\nSize of Contig Array:" << ct.name.size() * 2 + 1 << std::endl;
 
 	std::cout << "\n=>Storing Kmers from Contig ends... " << stamp() << std::endl;
-	std::vector<Gpu> gpus(params.gpus);
 	arks_index_stats ist{};
-	const double t_index0 = now();
+	t_index0 = now();
 	for (int d = 0; d < params.gpus; ++d) {
 		Gpu& g = gpus[d];
 		// ARKS_GPUS_SAME_DEVICE=1 (tests): every shard on device 0
 		const int dev = getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d;
+		const double tc0 = now();
 		int rc = arks_create(dev, params.k_value, end_bases.size() + 64, &g.h);
+		t_gpu_init += now() - tc0;
 		if (rc != ARKS_OK)
 			die(std::string("error: cannot initialise GPU ") + std::to_string(d) + ": " + arks_last_error(nullptr));
 		if (!end_conreci.empty())
@@ -901,7 +1188,7 @@ int main(int argc, char** argv)
 		if (any)
 			ck(g.h, arks_set_conreci_remap(g.h, remap.data(), (uint32_t)remap.size()), "arks_set_conreci_remap");
 	}
-	const double t_index1 = now();
+	t_index1 = now();
 	end_bases.clear();
 	end_bases.shrink_to_fit();
 	if (params.verbose)
@@ -915,7 +1202,7 @@ int main(int argc, char** argv)
 
 	// ---- reads: chromiumRead (Arcs.cpp:1132-1351)
 	std::cout << "\n=>Reading Chromium FASTQ file(s)... " << stamp() << std::endl;
-	const double t_map0 = now();
+	t_map0 = now();
 	size_t skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0;
 	size_t fast_blocks = 0;
 	{
@@ -1017,7 +1304,7 @@ int main(int argc, char** argv)
 		for (size_t i = 0; i < sizeof(mst) / 8; ++i)
 			a[i] += b[i];
 	}
-	const double t_map1 = now();
+	t_map1 = now();
 	if (params.verbose) {
 		printf("Stored read pairs: %llu\nSkipped invalid read pairs: %llu\nSkipped unpaired reads: %zu\nSkipped reads pairs without a "
 		       "good contig: %llu\n",
@@ -1039,6 +1326,8 @@ int main(int argc, char** argv)
 		       "parallel\n",
 		    t_map1 - t_map0, kmers / std::max(1e-9, t_map1 - t_map0), t_index1 - t_index0, fast_blocks);
 	}
+
+	} // ARKS
 
 	// ---- pairContigs (Arcs.cpp:1378-1435) on the GPU
 	std::cout << "\n=> Pairing scaffolds... " << stamp();
@@ -1350,8 +1639,8 @@ int main(int argc, char** argv)
 			f << x.first << '\t' << x.second << '\n';
 	}
 	if (params.verbose)
-		printf("wall-clock: start -> _original.gv closed %.3f s (index %.3f s, reads %.3f s)\n", t_gv - t_start, t_index1 - t_index0,
-		    t_map1 - t_map0);
+		printf("wall-clock: start -> _original.gv closed %.3f s (index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s)\n",
+		    t_gv - t_start, t_index1 - t_index0, t_gpu_init, t_map1 - t_map0);
 	for (auto& gp : gpus) {
 		for (auto& b : gp.batch) {
 			if (!b.bases)

@@ -46,6 +46,11 @@ chk Arcs/Arcs.cpp 1133 'chromiumRead'
 chk Arcs/Arcs.cpp 1379 'pairContigs'
 chk Arcs/Arcs.cpp 1460 'checkSignificance'
 chk Arcs/Arcs.cpp 1710 'writeTSV'
+chk Arcs/Arcs.cpp 206 'checkFlag'
+chk Arcs/Arcs.cpp 280 'calcSequenceIdentity'
+chk Arcs/Arcs.cpp 573 'readBAM'
+chk Arcs/Arcs.cpp 771 '^}'
+chk Arcs/Arcs.cpp 800 'readBAMS'
 chk Arcs/DistanceEst.h 16 'struct DistanceEstimate'
 chk Arcs/DistanceEst.h 102 'calcDistSamples'
 chk Arcs/DistanceEst.h 338 'estimateDistance'
@@ -62,6 +67,10 @@ x() { sed -n "${2},${3}p" "$REF/$1"; }
 # (types, calcDistSamples, buildJaccardToDist, buildPairToBarcodeStats, estimateDistance, the
 # samples writer); addEdgeDistances / writeDistTSV are restated over the driver's own graph
 { x Arcs/DistanceEst.h 15 389; x Arcs/DistanceEst.h 495 535; } > "$TMP/ref_dist.inc"
+# ARCS alignment mode: the SAM record loop that fills the IndexMap (checkFlag, checkChar,
+# calcSequenceIdentity, readBAM, readBAMS); getScaffSizes (DataLayer/FastaReader needs the autotools
+# config.h) is restated in the driver over kseq
+{ x Arcs/Arcs.cpp 204 220; x Arcs/Arcs.cpp 275 315; x Arcs/Arcs.cpp 572 771; x Arcs/Arcs.cpp 799 812; } > "$TMP/ref_sam.inc"
 
 g++ -std=c++11 -O2 -fopenmp -w -I"$TMP" -I"$REF" -I"$REF/Common" -I"$REF/Arcs" \
     "$HERE/ref_driver.cpp" "$REF/Common/ReadsProcessor.cpp" -lz -o "$OUT/arcs_ref"

@@ -39,7 +39,9 @@
 #include "Common/MapUtil.h"
 #include "Common/PairHash.h"
 #include "Common/ReadsProcessor.h"
+#include "Common/SAM.h"
 #include "Common/StatUtil.h"
+#include "Common/StringUtil.h"
 #include "kseq.h"
 #include <array>
 using std::ofstream;
@@ -71,6 +73,19 @@ bestContig_traced(ARCS::ContigKMap& kmap, std::string readseq, int k, double j, 
 #include "ref_part_b.inc" // getContigKmers .. checkSignificance, TSV writers
 #undef bestContig
 #include "ref_dist.inc" // DistanceEst.h minus the Boost-graph functions
+#include "ref_sam.inc"  // alignment mode: checkFlag .. readBAMS
+
+// getScaffSizes (Arcs.cpp:549-568) over kseq instead of DataLayer/FastaReader: contig id -> length
+static void
+getScaffSizesKseq(const std::string& file, ARCS::ContigToLength& contigToLength)
+{
+	gzFile fp = gzopen(file.c_str(), "r");
+	kseq_t* seq = kseq_init(fp);
+	while (kseq_read(seq) >= 0)
+		contigToLength[seq->name.s] = (int)seq->seq.l;
+	kseq_destroy(seq);
+	gzclose(fp);
+}
 
 // ---- Boost-free createGraph / removeDegreeNodes / write_graphviz restatement ----
 struct RefEdge
@@ -244,10 +259,11 @@ main(int argc, char** argv)
 		                                { "dist_tsv", required_argument, NULL, 1009 },
 		                                { "samples_tsv", required_argument, NULL, 1010 },
 		                                { "dist_est", no_argument, NULL, 'D' },
+		                                { "arcs", no_argument, NULL, 1011 },
 		                                { "bin_size", required_argument, NULL, 'B' },
 		                                { NULL, 0, NULL, 0 } };
 	params.arks = true;
-	for (int c; (c = getopt_long(argc, argv, "f:c:l:z:b:m:d:e:r:vt:u:j:k:DB:", lo, NULL)) != -1;) {
+	for (int c; (c = getopt_long(argc, argv, "f:c:l:z:b:m:d:e:r:vt:u:j:k:DB:s:", lo, NULL)) != -1;) {
 		std::istringstream arg(optarg != NULL ? optarg : "");
 		switch (c) {
 		case 'u': arg >> params.multfile; break;
@@ -282,12 +298,14 @@ main(int argc, char** argv)
 		case 1009: params.dist_tsv = optarg; break;
 		case 1010: params.dist_samples_tsv = optarg; break;
 		case 'D': params.dist_est = true; break;
+		case 1011: params.arks = false; break;
+		case 's': arg >> params.seq_id; break;
 		case 'B': arg >> params.dist_bin_size; break;
 		default: return 2;
 		}
 	}
 	std::vector<std::string> filenames(argv + optind, argv + argc);
-	if (params.file.empty() || filenames.empty() || params.base_name.empty()) {
+	if ((params.arks && params.file.empty()) || filenames.empty() || params.base_name.empty()) {
 		fprintf(stderr, "usage: arcs_ref -f contigs.fa -b base [arcs --arks options] reads.fq[.gz]...\n");
 		return 2;
 	}
@@ -301,20 +319,26 @@ main(int argc, char** argv)
 	ARCS::ContigToLength contigToLength;
 	std::vector<ARCS::CI> contigRecord;
 
-	double t0 = now();
-	if (!params.multfile.empty())
-		createIndexMultMap(params.multfile, indexMultMap);
-	else
-		readBarcodes(filenames, indexMultMap);
-	double t1 = now();
-	contigRecord.resize(initContigArray(params.file));
-	getContigKmers(params.file, kmap, contigRecord, contigToLength);
-	double t2 = now();
-	if (!dump_trace.empty())
-		g_trace = fopen(dump_trace.c_str(), "w");
-	readChroms(filenames, kmap, imap, indexMultMap, contigRecord);
-	if (g_trace)
-		fclose(g_trace);
+	double t0 = now(), t1 = t0, t2 = t0;
+	if (!params.arks) { // alignment mode, runArcs :1859-1871
+		if (!params.file.empty())
+			getScaffSizesKseq(params.file, contigToLength);
+		readBAMS(filenames, imap, indexMultMap, contigToLength);
+	} else {
+		if (!params.multfile.empty())
+			createIndexMultMap(params.multfile, indexMultMap);
+		else
+			readBarcodes(filenames, indexMultMap);
+		t1 = now();
+		contigRecord.resize(initContigArray(params.file));
+		getContigKmers(params.file, kmap, contigRecord, contigToLength);
+		t2 = now();
+		if (!dump_trace.empty())
+			g_trace = fopen(dump_trace.c_str(), "w");
+		readChroms(filenames, kmap, imap, indexMultMap, contigRecord);
+		if (g_trace)
+			fclose(g_trace);
+	}
 	double t3 = now();
 	pairContigs(imap, pmap, indexMultMap);
 	double t4 = now();

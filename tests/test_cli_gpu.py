@@ -86,8 +86,14 @@ def test_cli_matches_reference_code(argsfile, mode, tmp_path):
     tag = os.path.basename(argsfile)[len("expected_"):-len("_args.json")]
     spec = json.load(open(argsfile))
     exp = os.path.join(d, "expected_" + tag)
-    args = ["--arks", "-f", os.path.join(d, "draft.fa"), "-b", str(tmp_path / "o"), "--barcode-counts", str(tmp_path / "bc.tsv"),
-            "-P"] + spec["args"]
+    arcs_mode = spec.get("mode") == "arcs"  # alignment mode (SAM text in, Arcs.cpp:572-771)
+    if arcs_mode and mode != "one-pass":
+        pytest.skip("read-ingest modes do not apply to alignment input")
+    args = ["-b", str(tmp_path / "o"), "--barcode-counts", str(tmp_path / "bc.tsv"), "-P"] + spec["args"]
+    if not arcs_mode:
+        args = ["--arks", "-f", os.path.join(d, "draft.fa")] + args
+    elif spec.get("with_f"):
+        args = ["-f", os.path.join(d, "draft.fa")] + args
     if spec["multfile"]:
         args += ["-u", os.path.join(d, spec["multfile"])]
     dist = "-D" in spec["args"]
@@ -99,7 +105,7 @@ def test_cli_matches_reference_code(argsfile, mode, tmp_path):
     if mode == "2gpu-ids":
         # exercises the barcode-sharded multi-handle path; with one physical GPU both shards land on device 0
         env_gpus = "2"
-    args.append(os.path.join(d, "reads.fq.gz"))
+    args.append(os.path.join(d, "aln.sam" if arcs_mode else "reads.fq.gz"))
     env = dict(os.environ)
     if env_gpus:
         env["ARKS_GPUS"] = env_gpus

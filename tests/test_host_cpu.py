@@ -264,3 +264,19 @@ def test_parallel_ingest_with_known_multiplicities(tmp_path):
     got, fast = _ingest("par", path, 3, 2000, mult)
     assert got == want and fast > 0
     assert b"invalidbarcode=0" not in got.split(b"COUNTERS")[1].split(b"\n")[0]
+
+
+def test_parse_bx_tag_known_answers():
+    """the reference's own unit test of the SAM tag parser (Test/SAMTest.cpp:8-15), applied to the FASTQ-comment
+    rule of ingest.h (first BX:Z: tag up to the next blank) -- on these vectors the two rules agree"""
+    _build_ingest()
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = os.path.join(tmp, "t.fq")
+        with open(fq, "w") as f:
+            f.write("@r1/1 QT:Z:AA<FFKKK BX:Z:CGTCAGGTCAGAGGTG-1 XT:i:0\nACGT\n+\nIIII\n@r1/2 QT:Z:AA<FFKKK BX:Z:CGTCAGGTCAGAGGTG-1 XT:i:0\nACGT\n+\nIIII\n"
+                    "@r2/1 QT:Z:AA<FFKKK XT:i:0\nACGT\n+\nIIII\n@r2/2 QT:Z:AA<FFKKK XT:i:0\nACGT\n+\nIIII\n")
+        out, _ = _ingest("seq", fq)
+        assert out.split(b"\n")[0] == b"P\tCGTCAGGTCAGAGGTG-1\tACGT\tACGT"
+        assert b"emptybarcode=1" in out
+        assert _ingest("par", fq, 2, 64)[0] == out

@@ -126,11 +126,96 @@ def add_dist_cases():
     run_ref(d, ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "5000", "-z", "500", "-r", "0.05", "-t", "1", "-D"], "d")
 
 
+def make_sam_case():
+    """ARCS alignment mode (Arcs.cpp:572-771): synthetic SAM text with consecutive read pairs and the record
+    shapes the state machine distinguishes; expected outputs from the reference's own readBAM code"""
+    rng = np.random.default_rng(21)
+    d = os.path.join(OUT, "sam_arcs")
+    os.makedirs(d, exist_ok=True)
+    lens = [9000, 14000, 400, 7000, 30000, 12000, 8000, 5200]
+    names = ["10", "9", "tiny", "2", "b", "a", "100", "1"]
+    acgt = "ACGT"
+    with open(os.path.join(d, "draft.fa"), "w") as f:
+        for nm, L in zip(names, lens):
+            f.write(">%s len=%d\n%s\n" % (nm, L, "".join(acgt[int(x)] for x in rng.integers(0, 4, L))))
+    lines = ["@HD\tVN:1.5\tSO:unsorted"] + ["@SQ\tSN:%s\tLN:%d" % (nm, L) for nm, L in zip(names, lens)] + ["@PG\tID:bwa\tPN:bwa"]
+    n_bc, ppb = 90, 30
+    t = 0
+    for b in range(n_bc):
+        code = "".join(acgt[(b >> (2 * (7 - q))) & 3] for q in range(8))
+        c1 = int(rng.integers(0, len(names)))
+        c2 = (c1 + 1 + int(rng.integers(0, 2))) % len(names)  # a molecule spans the ends of two contigs
+        ends = {c1: rng.random() < 0.5, c2: rng.random() < 0.5}
+        for p in range(ppb):
+            c = c1 if p % 2 == 0 else c2
+            L = lens[c]
+            end_head = ends[c] if rng.random() < 0.9 else not ends[c]
+            pos = int(rng.integers(1, max(2, min(2500, L // 2)))) if end_head else int(L - rng.integers(min(150, L // 4), max(min(150, L // 4) + 1, min(2600, L // 2))))
+            pos2 = pos + int(rng.integers(150, 400))
+            fl = (99, 147) if rng.random() < 0.5 else (83, 163)
+            rn = "r%d" % t
+            tags = "NM:i:%d\tBX:Z:%s-1\tQT:Z:IIII" % (int(rng.integers(0, 3)), code)
+            cig = ["150M", "100M2I48M", "5S145M", "60M1D90M", "75=1X74="][int(rng.integers(0, 5))]
+            seq = "".join(acgt[int(x)] for x in rng.integers(0, 4, 150))
+            rec = [[rn, fl[0], names[c], pos, 60, cig, "=", pos2, 300, seq, "I" * 150, tags],
+                   [rn, fl[1], names[c], pos2, 60, "150M", "=", pos, -300, seq[::-1], "I" * 150, tags]]
+            k = t % 23
+            if k == 1:
+                for r in rec:
+                    r[0], r[11] = "q%d_%s" % (t, code), "NM:i:1"  # barcode from the read name
+            elif k == 2:
+                for r in rec:
+                    r[0], r[11] = "q%d_ACGTNX" % t, "NM:i:1"  # not a barcode
+            elif k == 3:
+                rec[0][4] = 0  # MAPQ 0
+            elif k == 4:
+                rec[1][11] = "NM:i:25\tBX:Z:%s-1" % code  # low identity
+            elif k == 5:
+                rec[1][2] = names[(c + 1) % len(names)]  # mates on different contigs
+            elif k == 6:
+                rec[0][2] = rec[1][2] = "*"
+            elif k == 7:
+                rec.append([rn, 2048 + fl[0], names[c], pos + 50, 60, "80M70H", "=", pos2, 0, seq[:80], "I" * 80, tags])  # third line
+            elif k == 8:
+                rec = rec[:1]  # singleton
+            elif k == 9:
+                rec[0][1], rec[1][1] = 65, 129  # not proper pairs
+            elif k == 10:
+                rec[0][1] |= 256  # secondary: not counted in the multiplicity, pair rejected by the flag test
+            elif k == 11:
+                rec[0][3], rec[1][3] = L // 2 - 100, L // 2 + 100  # middle of the contig
+            elif k == 12:
+                rec[1][11] = "XA:Z:foo BX:Z:%s-1 XT:i:0" % code  # blank-separated tags
+            elif k == 13:
+                rec[0][5] = "*"  # no CIGAR: identity 0
+            for r in rec:
+                lines.append("\t".join(str(x) for x in r))
+            t += 1
+    lines.append("")
+    with open(os.path.join(d, "aln.sam"), "w") as f:
+        f.write("\n".join(lines))
+    for tag, args, with_f in (
+            ("a", ["-s", "98", "-c", "2", "-m", "4-10000", "-e", "3000", "-z", "500", "-r", "0.05", "-l", "0"], True),
+            ("b", ["-s", "90", "-c", "3", "-m", "10-10000", "-e", "0", "-z", "1000", "-r", "0.1", "-l", "2", "-d", "3", "-D", "-B", "4"], False)):
+        base = os.path.join(d, "expected_" + tag)
+        cmd = [REF, "--arcs", "-b", base, "--tsv", base + "_main.tsv", "--barcode-counts", base + "_bc.tsv", "--dump-imap",
+               base + "_imap.txt", "--dump-pmap", base + "_pmap.txt", "--timing-json", base + "_stats.json"] + args
+        if with_f:
+            cmd += ["-f", os.path.join(d, "draft.fa")]
+        if "-D" in args:
+            cmd += ["--dist_tsv", base + "_dist.tsv", "--samples_tsv", base + "_samples.tsv"]
+        cmd.append(os.path.join(d, "aln.sam"))
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        json.dump({"args": args, "multfile": None, "mode": "arcs", "with_f": with_f}, open(base + "_args.json", "w"))
+
+
 def main():
     if not os.path.exists(REF):
         raise SystemExit("oracle/_ref/arcs_ref is missing: run oracle/build_ref.sh where /root/reference exists")
     if len(sys.argv) > 1 and sys.argv[1] == "dist":
         return add_dist_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "sam":
+        return make_sam_case()
     # case A: k=30 defaults-ish, adversarial FASTQ, contig names whose string order differs from numeric order
     names = ["10", "9", "100", "2", "b", "a", "2", "11", "1", "3"]  # "2" appears twice
     d = make_case("mixed_k30", 11, 30, contig_names=names, fastq_mutator=mutate, n_barcodes=120, ppb=60, mol_len=9000, mols=1)
@@ -151,6 +236,7 @@ def main():
     d = make_case("long_k20", 13, 20, genome_len=100000, mean_contig=20000, n_barcodes=300, ppb=12, read_len=250, jitter=0, mol_len=15000, mols=1)
     run_ref(d, ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
     add_dist_cases()
+    make_sam_case()
     print("fixtures written under", OUT)
     subprocess.call(["du", "-sh", OUT])
 
