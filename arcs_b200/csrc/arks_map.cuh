@@ -304,7 +304,13 @@ warp_probe_windows(const WarpRegion& R, uint32_t Lc, const uint16_t* list, uint3
 				uint32_t p = list ? list[i] : i;
 				act |= 1u << r;
 				key[r] = canonical_key<KW>(R.W, R.RC, p, P.k, Lp, P.mask_hi, P.mask_lo);
-				load_slot(P.table, hash_to_slot(key_hash<KW>(key[r]), P.nslots), hi[r], lo[r], val[r], pi);
+				const uint64_t h = key_hash<KW>(key[r]);
+				// the membership filter first: windows that end up here are mostly not in the draft at all
+				if (P.bloom && !bloom_maybe(P.bloom, bloom_probe(h, P.bloom_words))) {
+					act &= ~(1u << r);
+					continue;
+				}
+				load_slot(P.table, hash_to_slot(h, P.nslots), hi[r], lo[r], val[r], pi);
 			}
 		}
 		uint32_t hit[kProbeBatch];

@@ -480,7 +480,7 @@ def main():
             },
             "clocks": clk, "gpu_launches": int(gpu_launches), "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "map_groups_kernel<2> (lane-per-read, 92 % of the batch) + map_slow_kernel<2> (deferred mates); one batch", "bytes_per_kmer": BYTES_PER_KMER,
+                         "traffic": traffic, "kernel": "map_groups_kernel<2> (lane-per-read, 95 % of the batch) + map_slow_kernel<2> (deferred mates); one batch", "bytes_per_kmer": BYTES_PER_KMER,
                          "peak_source": peak_src, "launch_ms": launch_ms},
             "cpu_baseline": cpu,
         }
