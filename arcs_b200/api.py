@@ -49,7 +49,7 @@ SYMBOLS = [
     "arks_host_free", "arks_index_add", "arks_index_add_device", "arks_index_finalize", "arks_index_size",
     "arks_index_dump", "arks_set_conreci_remap", "arks_map_pairs", "arks_map_pairs_device", "arks_map_get_stats",
     "arks_map_stats_reset", "arks_imap_size", "arks_imap_export", "arks_imap_add", "arks_pair_links",
-    "arks_pmap_size", "arks_pmap_export", "arks_head_tail_table", "arks_launch_count",
+    "arks_pmap_size", "arks_pmap_export", "arks_head_tail_table", "arks_launch_count", "arks_device_init",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library():
     L.arks_sync.argtypes = [vp]
     L.arks_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.arks_host_free.argtypes = [vp]
+    L.arks_device_init.argtypes = [C.c_int]
     L.arks_index_add.argtypes = [vp, vp, u64p, u32p, C.c_uint32]
     L.arks_index_add_device.argtypes = [vp, vp, vp, vp, u64p, C.c_uint32]
     L.arks_index_finalize.argtypes = [vp, C.POINTER(IndexStats)]

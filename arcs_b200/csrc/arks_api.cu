@@ -8,6 +8,7 @@
 #include "arks_map.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -477,7 +478,20 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 	h->k = k;
 	h->kw = k <= 32 ? 1 : 2;
 	key_masks(k, h->mask_hi, h->mask_lo);
+	// ARKS_TIMING=1: where the start-up time goes (context creation, table allocation, ...)
+	const bool timing = getenv("ARKS_TIMING") != nullptr;
+	auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_last = tnow();
+	auto lap = [&](const char* what) {
+		if (timing) {
+			const double t = tnow();
+			fprintf(stderr, "arks_create: %-28s %.3f s\n", what, t - t_last);
+			t_last = t;
+		}
+	};
 	CUC(cudaSetDevice(device));
+	CUC(cudaFree(0));
+	lap("context");
 	cudaDeviceProp prop;
 	CUC(cudaGetDeviceProperties(&prop, device));
 	if (prop.major < 10) {
@@ -519,7 +533,9 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		h->bloom_bits_per_key = std::max(0, std::min(64, atoi(s)));
 	if (const char* s = getenv("ARKS_LANE_GENERAL"))
 		h->lane_general = atoi(s) ? 1 : 0;
+	lap("streams, events, limits");
 	CUC(cudaMalloc(&h->table, h->nslots * slot_bytes));
+	lap("table cudaMalloc");
 	CUC(cudaMemsetAsync(h->table, 0xFF, h->nslots * slot_bytes, h->stream));
 	CUC(cudaMalloc(&h->d_ictr, sizeof(IndexCounters)));
 	CUC(cudaMemsetAsync(h->d_ictr, 0, sizeof(IndexCounters), h->stream));
@@ -572,7 +588,9 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		if (const char* s = getenv("ARKS_MAP_MODE"))
 			h->map_mode_pair = strcmp(s, "pair") == 0;
 	}
+	lap("small buffers, occupancy");
 	CUC(cudaStreamSynchronize(h->stream));
+	lap("table fill");
 #undef CUC
 	*out = h;
 	return ARKS_OK;
@@ -643,6 +661,14 @@ int arks_host_alloc(void** p, size_t bytes)
 	if (!p)
 		return ARKS_E_ARG;
 	CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+	return ARKS_OK;
+}
+
+int arks_device_init(int device)
+{
+	arks_handle* h = nullptr;
+	CU(cudaSetDevice(device));
+	CU(cudaFree(0));
 	return ARKS_OK;
 }
 

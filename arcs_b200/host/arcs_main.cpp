@@ -1091,6 +1091,11 @@ int main(int argc, char** argv)
 			ck(g.h, arks_imap_add(g.h, rb.data(), rc.data(), rh.data(), rt.data(), rb.size()), "arks_imap_add");
 		t_map1 = now();
 	} else {
+	// the CUDA context is created on a helper thread while the multiplicity file and the draft are parsed
+	std::thread gpu_init([] {
+		for (int d = 0; d < params.gpus; ++d)
+			arks_device_init(getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d);
+	});
 	// ---- barcode multiplicities
 	const bool have_multfile = !params.multfile.empty();
 	// `goodmult = mult > min || mult < max` (Arcs.cpp:1267) can only be false for an inverted range
@@ -1162,6 +1167,7 @@ int main(int argc, char** argv)
 		std::cerr << "Number of contigs:" << ct.name.size() << "\nSize of Contig Array:" << ct.name.size() * 2 + 1 << std::endl;
 
 	std::cout << "\n=>Storing Kmers from Contig ends... " << stamp() << std::endl;
+	gpu_init.join();
 	arks_index_stats ist{};
 	t_index0 = now();
 	for (int d = 0; d < params.gpus; ++d) {

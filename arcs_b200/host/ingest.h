@@ -422,92 +422,207 @@ struct ParallelIngestOptions
 	std::vector<PairBatch> slots;
 };
 
-// Reads `path` (plain or gzip) block-wise.  Regular blocks are committed in file order through
-// sink.submit (after the block-local barcode ids have been replaced by global ones); from the first
-// irregular block on, and for the tail of the file, the bytes go through ingest_sequential.
-// Returns false if the file cannot be opened.
-inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const IngestConfig& cfg, bool& counting, IngestCounters& ctr,
-    PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr)
+// Reads a file (plain or gzip) block-wise.  start() opens it and launches the reader and the parser
+// threads, which run ahead by as many blocks as there are slots (the caller can do something else in the
+// meantime -- the CLI builds the k-mer index on the GPU); finish() commits the regular blocks in file order
+// through sink.submit (after the block-local barcode ids have been replaced by global ones) and, from the
+// first irregular block on and for the tail of the file, sends the bytes through ingest_sequential.
+class ParallelIngest
 {
-	// plain regular files are memory-mapped (blocks are cut in place, nothing is copied); gzip files and
-	// pipes go through zlib (transparent for plain data) into block buffers
-	int fd = ::open(path.c_str(), O_RDONLY);
-	if (fd < 0)
-		return false;
-	gzFile gz = nullptr;
-	const char* map = nullptr;
-	size_t map_size = 0;
+  public:
+	ParallelIngest() = default;
+	ParallelIngest(const ParallelIngest&) = delete;
+	ParallelIngest& operator=(const ParallelIngest&) = delete;
+	~ParallelIngest()
 	{
+		if (m_started && !m_finished)
+			abort_threads();
+	}
+
+	// `frozen` (only with cfg.mult_known): the barcode table, which must not change until finish() returns.
+	// Returns false if the file cannot be opened.
+	bool start(const std::string& path, const IngestConfig& cfg, const ParallelIngestOptions& opt, const Barcodes* frozen)
+	{
+		m_cfg = cfg;
+		m_opt = opt;
+		m_frozen = frozen;
+		// plain regular files are memory-mapped (blocks are cut in place, nothing is copied); gzip files and
+		// pipes go through zlib (transparent for plain data) into block buffers
+		m_fd = ::open(path.c_str(), O_RDONLY);
+		if (m_fd < 0)
+			return false;
 		unsigned char magic[2] = { 0, 0 };
 		struct stat st;
-		const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
-		const bool plain = regular && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b);
+		const bool regular = fstat(m_fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
+		const bool plain = regular && pread(m_fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b);
 		if (plain) {
-			void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, m_fd, 0);
 			if (m != MAP_FAILED) {
-				map = (const char*)m;
-				map_size = (size_t)st.st_size;
-				madvise(m, map_size, MADV_SEQUENTIAL);
+				m_map = (const char*)m;
+				m_map_size = (size_t)st.st_size;
+				madvise(m, m_map_size, MADV_SEQUENTIAL);
 			}
 		}
-		if (!map) {
-			gz = gzdopen(fd, "r");
-			if (!gz) {
-				::close(fd);
+		if (!m_map) {
+			m_gz = gzdopen(m_fd, "r");
+			if (!m_gz) {
+				::close(m_fd);
+				m_fd = -1;
 				return false;
 			}
-			gzbuffer(gz, 1u << 20);
+			gzbuffer(m_gz, 1u << 20);
 		}
+		m_bufs.resize(m_opt.slots.size());
+		for (size_t i = 0; i < m_opt.slots.size(); ++i)
+			m_free_slots.push_back((int)i);
+		m_started = true;
+		m_reader = std::thread([this] { reader_loop(); });
+		for (int w = 0; w < std::max(1, m_opt.workers); ++w)
+			m_workers.emplace_back([this] { worker_loop(); });
+		return true;
 	}
-	size_t map_pos = 0; // mapped files: first byte that has not been cut into a block (reader thread)
-	auto read_some = [&](char* dst, size_t n) -> long { return gzread(gz, dst, (unsigned)std::min<size_t>(n, 1u << 30)); };
 
-	const size_t n_slots = opt.slots.size();
-	std::vector<std::vector<char>> bufs(n_slots);
-	std::mutex mu;
-	std::condition_variable cv;
-	std::deque<std::unique_ptr<Block>> todo;           // cut, waiting for a worker
-	std::map<uint64_t, std::unique_ptr<Block>> parsed;  // parsed, waiting for their turn
-	std::vector<int> free_slots;
-	for (size_t i = 0; i < n_slots; ++i)
-		free_slots.push_back((int)i);
-	bool reader_done = false, stop = false;
-	std::string tail; // bytes after the last block the reader cut
-	uint64_t n_cut = 0;
+	void finish(Barcodes& bc, bool& counting, IngestCounters& ctr, PairSink& sink, size_t* n_fast_blocks = nullptr)
+	{
+		// committer (this thread): blocks in file order
+		uint64_t next = 0;
+		size_t n_fast = 0;
+		std::vector<uint32_t> gid;
+		std::unique_ptr<Block> irregular;
+		for (;;) {
+			std::unique_ptr<Block> b;
+			{
+				std::unique_lock<std::mutex> lk(m_mu);
+				m_cv.wait(lk, [&] { return m_parsed.count(next) || (m_reader_done && next >= m_n_cut); });
+				if (!m_parsed.count(next))
+					break; // everything that was cut has been committed
+				b = std::move(m_parsed[next]);
+				m_parsed.erase(next);
+			}
+			if (!b->regular) {
+				// stop cutting; this block and everything behind it is re-read by the faithful reader
+				{
+					std::lock_guard<std::mutex> lk(m_mu);
+					m_stop = true;
+				}
+				m_cv.notify_all();
+				irregular = std::move(b);
+				break;
+			}
+			// multiplicities and global barcode ids
+			if (!m_cfg.mult_known) {
+				gid.resize(b->local_barcodes.size());
+				for (size_t i = 0; i < gid.size(); ++i) {
+					gid[i] = bc.intern(b->local_barcodes[i]);
+					if (counting) {
+						bc.mult[gid[i]] += b->local_counts[i];
+						bc.counted[gid[i]] = 1;
+					}
+				}
+				for (uint32_t i = 0; i < b->out.n_pairs; ++i)
+					b->out.bc[i] = gid[b->out.bc[i]];
+			}
+			if (!b->messages.empty())
+				std::cout << b->messages << std::flush;
+			ctr.skipped_unpaired += b->skipped_unpaired;
+			ctr.emptybarcode += b->emptybarcode;
+			ctr.invalidbarcode += b->invalidbarcode;
+			ctr.skipped_badmult += b->skipped_badmult;
+			const size_t before = ctr.count;
+			ctr.count += b->records; // the reference adds 2 per pair of records
+			if (m_cfg.verbose)
+				for (size_t c = (before / 10000000 + 1) * 10000000; c <= ctr.count; c += 10000000)
+					std::cout << "Processed " << c << " read pairs." << std::endl;
+			if (b->out.n_pairs)
+				sink.submit(b->out);
+			n_fast++;
+			{
+				std::lock_guard<std::mutex> lk(m_mu);
+				m_free_slots.push_back(b->slot);
+			}
+			m_cv.notify_all();
+			next++;
+		}
+		abort_threads();
+		// the bytes that did not go through the block path, in file order: the irregular block, the blocks that
+		// were already cut behind it, and the tail the reader holds; then whatever is still in the stream
+		std::string prefix;
+		if (irregular) {
+			std::map<uint64_t, std::unique_ptr<Block>> rest;
+			for (auto& kv : m_parsed)
+				rest[kv.first] = std::move(kv.second);
+			for (auto& b : m_todo)
+				rest[b->seq] = std::move(b);
+			prefix.assign(irregular->data, irregular->size);
+			for (auto& kv : rest)
+				prefix.append(kv.second->data, kv.second->size);
+		}
+		prefix += m_tail;
+		if (n_fast_blocks)
+			*n_fast_blocks = n_fast;
+		if (m_map) {
+			// mapped file: the stream continues behind the last block that was cut (zlib reads plain data as is)
+			munmap((void*)m_map, m_map_size);
+			m_map = nullptr;
+			lseek(m_fd, (off_t)m_map_pos, SEEK_SET);
+			m_gz = gzdopen(m_fd, "r");
+		}
+		SeqReader rd(m_gz, std::move(prefix)); // takes the stream over (and closes it)
+		m_gz = nullptr;
+		m_fd = -1;
+		m_finished = true;
+		ingest_sequential(rd, bc, m_cfg, counting, ctr, sink);
+	}
 
-	// reader: cuts blocks of whole pairs = multiples of 8 lines (only meaningful for strict files;
-	// anything else is caught by parse_block and sent down the sequential path)
-	std::thread reader([&] {
+  private:
+	void abort_threads()
+	{
+		{
+			std::lock_guard<std::mutex> lk(m_mu);
+			m_stop = true;
+		}
+		m_cv.notify_all();
+		if (m_reader.joinable())
+			m_reader.join();
+		for (auto& t : m_workers)
+			if (t.joinable())
+				t.join();
+	}
+
+	// cuts blocks of whole pairs = multiples of 8 lines (only meaningful for strict files; anything else is
+	// caught by parse_block and sent down the sequential path)
+	void reader_loop()
+	{
 		std::string carry;
 		uint64_t seqno = 0;
 		bool eof = false;
-		size_t span = opt.block_bytes; // mapped files: bytes looked at for the next block
+		size_t span = m_opt.block_bytes; // mapped files: bytes looked at for the next block
 		while (!eof) {
 			int slot;
 			{
-				std::unique_lock<std::mutex> lk(mu);
-				cv.wait(lk, [&] { return stop || !free_slots.empty(); });
-				if (stop)
+				std::unique_lock<std::mutex> lk(m_mu);
+				m_cv.wait(lk, [&] { return m_stop || !m_free_slots.empty(); });
+				if (m_stop)
 					break;
-				slot = free_slots.back();
-				free_slots.pop_back();
+				slot = m_free_slots.back();
+				m_free_slots.pop_back();
 			}
 			const char* base;
 			size_t have;
-			if (map) {
-				base = map + map_pos;
-				have = std::min(span, map_size - map_pos);
-				eof = map_pos + have == map_size;
+			if (m_map) {
+				base = m_map + m_map_pos;
+				have = std::min(span, m_map_size - m_map_pos);
+				eof = m_map_pos + have == m_map_size;
 			} else {
-				std::vector<char>& buf = bufs[(size_t)slot];
-				if (buf.size() < carry.size() + opt.block_bytes)
-					buf.resize(carry.size() + opt.block_bytes);
+				std::vector<char>& buf = m_bufs[(size_t)slot];
+				if (buf.size() < carry.size() + m_opt.block_bytes)
+					buf.resize(carry.size() + m_opt.block_bytes);
 				memcpy(buf.data(), carry.data(), carry.size());
 				have = carry.size();
-				const size_t want = carry.size() + opt.block_bytes;
+				const size_t want = carry.size() + m_opt.block_bytes;
 				carry.clear();
 				while (have < want) {
-					long n = read_some(buf.data() + have, want - have);
+					const int n = gzread(m_gz, buf.data() + have, (unsigned)std::min<size_t>(want - have, 1u << 30));
 					if (n <= 0) {
 						eof = true;
 						break;
@@ -522,11 +637,9 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 			{
 				const size_t lines = count_newlines(base, have);
 				size_t drop = lines & 7u; // newlines after the last whole group
-				const char* e = base + have;
 				if (lines >= 8) {
-					// e moves to just behind the (lines - drop)-th newline
 					const char* last = (const char*)memrchr(base, '\n', have);
-					e = last + 1;
+					const char* e = last + 1;
 					while (drop--) {
 						last = (const char*)memrchr(base, '\n', (size_t)(last - base));
 						e = last + 1;
@@ -534,19 +647,19 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 					cut = (size_t)(e - base);
 				}
 			}
-			if (map) {
-				map_pos += cut;
-				span = cut ? opt.block_bytes : span + opt.block_bytes; // no whole pair in sight: look further
+			if (m_map) {
+				m_map_pos += cut;
+				span = cut ? m_opt.block_bytes : span + m_opt.block_bytes; // no whole pair in sight: look further
 			} else {
 				carry.assign(base + cut, have - cut);
 			}
 			if (cut == 0) {
-				std::lock_guard<std::mutex> lk(mu);
-				free_slots.push_back(slot);
-				if (!eof && (map ? span : carry.size()) > 4 * opt.block_bytes) // lines longer than a block: not the strict shape
-					stop = true;
-				cv.notify_all();
-				if (stop)
+				std::lock_guard<std::mutex> lk(m_mu);
+				m_free_slots.push_back(slot);
+				if (!eof && (m_map ? span : carry.size()) > 4 * m_opt.block_bytes) // lines longer than a block: not the strict shape
+					m_stop = true;
+				m_cv.notify_all();
+				if (m_stop)
 					break;
 				continue;
 			}
@@ -555,133 +668,68 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
 			b->data = base;
 			b->size = cut;
 			b->slot = slot;
-			b->out = opt.slots[(size_t)slot];
+			b->out = m_opt.slots[(size_t)slot];
 			{
-				std::lock_guard<std::mutex> lk(mu);
-				todo.push_back(std::move(b));
-				n_cut = seqno;
+				std::lock_guard<std::mutex> lk(m_mu);
+				m_todo.push_back(std::move(b));
+				m_n_cut = seqno;
 			}
-			cv.notify_all();
+			m_cv.notify_all();
 		}
-		std::lock_guard<std::mutex> lk(mu);
-		tail.swap(carry);
-		reader_done = true;
-		cv.notify_all();
-	});
-
-	std::vector<std::thread> workers;
-	for (int w = 0; w < std::max(1, opt.workers); ++w)
-		workers.emplace_back([&] {
-			for (;;) {
-				std::unique_ptr<Block> b;
-				{
-					std::unique_lock<std::mutex> lk(mu);
-					cv.wait(lk, [&] { return !todo.empty() || reader_done || stop; });
-					if (todo.empty())
-						return;
-					b = std::move(todo.front());
-					todo.pop_front();
-				}
-				parse_block(*b, cfg, cfg.mult_known ? &bc : nullptr);
-				{
-					std::lock_guard<std::mutex> lk(mu);
-					parsed[b->seq] = std::move(b);
-				}
-				cv.notify_all();
-			}
-		});
-
-	// committer (this thread): blocks in file order
-	uint64_t next = 0;
-	size_t n_fast = 0;
-	std::vector<uint32_t> gid;
-	std::unique_ptr<Block> irregular;
-	for (;;) {
-		std::unique_ptr<Block> b;
-		{
-			std::unique_lock<std::mutex> lk(mu);
-			cv.wait(lk, [&] { return parsed.count(next) || (reader_done && next >= n_cut); });
-			if (!parsed.count(next))
-				break; // everything that was cut has been committed
-			b = std::move(parsed[next]);
-			parsed.erase(next);
-		}
-		if (!b->regular) {
-			// stop cutting; this block and everything behind it is re-read by the faithful reader
-			{
-				std::lock_guard<std::mutex> lk(mu);
-				stop = true;
-			}
-			cv.notify_all();
-			irregular = std::move(b);
-			break;
-		}
-		// multiplicities and global barcode ids
-		if (!cfg.mult_known) {
-			gid.resize(b->local_barcodes.size());
-			for (size_t i = 0; i < gid.size(); ++i) {
-				gid[i] = bc.intern(b->local_barcodes[i]);
-				if (counting) {
-					bc.mult[gid[i]] += b->local_counts[i];
-					bc.counted[gid[i]] = 1;
-				}
-			}
-			for (uint32_t i = 0; i < b->out.n_pairs; ++i)
-				b->out.bc[i] = gid[b->out.bc[i]];
-		}
-		if (!b->messages.empty())
-			std::cout << b->messages << std::flush;
-		ctr.skipped_unpaired += b->skipped_unpaired;
-		ctr.emptybarcode += b->emptybarcode;
-		ctr.invalidbarcode += b->invalidbarcode;
-		ctr.skipped_badmult += b->skipped_badmult;
-		const size_t before = ctr.count;
-		ctr.count += b->records; // the reference adds 2 per pair of records
-		if (cfg.verbose)
-			for (size_t c = (before / 10000000 + 1) * 10000000; c <= ctr.count; c += 10000000)
-				std::cout << "Processed " << c << " read pairs." << std::endl;
-		if (b->out.n_pairs)
-			sink.submit(b->out);
-		n_fast++;
-		{
-			std::lock_guard<std::mutex> lk(mu);
-			free_slots.push_back(b->slot);
-		}
-		cv.notify_all();
-		next++;
+		std::lock_guard<std::mutex> lk(m_mu);
+		m_tail.swap(carry);
+		m_reader_done = true;
+		m_cv.notify_all();
 	}
-	reader.join();
+
+	void worker_loop()
 	{
-		std::lock_guard<std::mutex> lk(mu);
-		stop = true;
+		for (;;) {
+			std::unique_ptr<Block> b;
+			{
+				std::unique_lock<std::mutex> lk(m_mu);
+				m_cv.wait(lk, [&] { return !m_todo.empty() || m_reader_done || m_stop; });
+				if (m_todo.empty())
+					return;
+				b = std::move(m_todo.front());
+				m_todo.pop_front();
+			}
+			parse_block(*b, m_cfg, m_cfg.mult_known ? m_frozen : nullptr);
+			{
+				std::lock_guard<std::mutex> lk(m_mu);
+				m_parsed[b->seq] = std::move(b);
+			}
+			m_cv.notify_all();
+		}
 	}
-	cv.notify_all();
-	for (auto& t : workers)
-		t.join();
-	// the bytes that did not go through the block path, in file order: the irregular block, the blocks that
-	// were already cut behind it, and the tail the reader holds; then whatever is still in the stream
-	std::string prefix;
-	if (irregular) {
-		std::map<uint64_t, std::unique_ptr<Block>> rest;
-		for (auto& kv : parsed)
-			rest[kv.first] = std::move(kv.second);
-		for (auto& b : todo)
-			rest[b->seq] = std::move(b);
-		prefix.assign(irregular->data, irregular->size);
-		for (auto& kv : rest)
-			prefix.append(kv.second->data, kv.second->size);
-	}
-	prefix += tail;
-	if (n_fast_blocks)
-		*n_fast_blocks = n_fast;
-	if (map) {
-		// mapped file: the stream continues behind the last block that was cut (zlib reads plain data as is)
-		munmap((void*)map, map_size);
-		lseek(fd, (off_t)map_pos, SEEK_SET);
-		gz = gzdopen(fd, "r");
-	}
-	SeqReader rd(gz, std::move(prefix)); // takes the stream over (and closes it)
-	ingest_sequential(rd, bc, cfg, counting, ctr, sink);
+
+	IngestConfig m_cfg;
+	ParallelIngestOptions m_opt;
+	const Barcodes* m_frozen = nullptr;
+	int m_fd = -1;
+	gzFile m_gz = nullptr;
+	const char* m_map = nullptr;
+	size_t m_map_size = 0, m_map_pos = 0; // m_map_pos: first byte that has not been cut into a block (reader thread)
+	std::vector<std::vector<char>> m_bufs;
+	std::mutex m_mu;
+	std::condition_variable m_cv;
+	std::deque<std::unique_ptr<Block>> m_todo;          // cut, waiting for a worker
+	std::map<uint64_t, std::unique_ptr<Block>> m_parsed; // parsed, waiting for their turn
+	std::vector<int> m_free_slots;
+	bool m_reader_done = false, m_stop = false, m_started = false, m_finished = false;
+	std::string m_tail; // bytes after the last block the reader cut
+	uint64_t m_n_cut = 0;
+	std::thread m_reader;
+	std::vector<std::thread> m_workers;
+};
+
+inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const IngestConfig& cfg, bool& counting, IngestCounters& ctr,
+    PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr)
+{
+	ParallelIngest pi;
+	if (!pi.start(path, cfg, opt, cfg.mult_known ? &bc : nullptr))
+		return false;
+	pi.finish(bc, counting, ctr, sink, n_fast_blocks);
 	return true;
 }
 

@@ -75,6 +75,10 @@ int arks_set_stream(arks_handle* h, void* cuda_stream);
 int arks_sync(arks_handle* h);
 /* Pinned host memory for the batch buffers passed to arks_index_add / arks_map_pairs. */
 int arks_host_alloc(void** p, size_t bytes);
+/* Creates the CUDA context of `device` (the half second to a second every CUDA process pays once).
+ * Optional: a host that has other start-up work (parsing the draft) can call it from a helper
+ * thread first so that arks_create does not wait for it. */
+int arks_device_init(int device);
 int arks_host_free(void* p);
 
 /* ---- kernel 1: contig-end k-mer index -------------------------------------------- */
