@@ -112,6 +112,23 @@ def run_ref(d, args, tag, multfile=None):
     json.dump({"args": args, "multfile": os.path.basename(multfile) if multfile else None}, open(base + "_args.json", "w"))
 
 
+def shuffle_pairs(recs, rng):
+    """stLFR-style input (BASELINE.json configs[2]): read pairs of all barcodes interleaved at random"""
+    order = rng.permutation(len(recs) // 2)
+    out = []
+    for i in order:
+        out += [recs[2 * i], recs[2 * i + 1]]
+    return out
+
+
+def add_shuffled_case():
+    # configs[2] shape: k=40, barcodes not grouped in the file, multiplicity filter -m 2-10000
+    d = make_case("shuffled_k40", 14, 40, fastq_mutator=shuffle_pairs, genome_len=100000, mean_contig=12000, n_barcodes=400,
+                  ppb=12, mol_len=14000, mols=1)
+    run_ref(d, ["-k", "40", "-j", "0.5", "-c", "2", "-m", "2-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
+    run_ref(d, ["-k", "40", "-j", "0.5", "-c", "3", "-m", "30-10000", "-e", "2000", "-z", "500", "-r", "0.05", "-t", "1", "-D"], "d")
+
+
 def add_dist_cases():
     """-D runs of the reference's code on the existing inputs (tags d*, added after the first fixtures)"""
     d = os.path.join(OUT, "mixed_k30")
@@ -216,6 +233,8 @@ def main():
         return add_dist_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "sam":
         return make_sam_case()
+    if len(sys.argv) > 1 and sys.argv[1] == "shuffled":
+        return add_shuffled_case()
     # case A: k=30 defaults-ish, adversarial FASTQ, contig names whose string order differs from numeric order
     names = ["10", "9", "100", "2", "b", "a", "2", "11", "1", "3"]  # "2" appears twice
     d = make_case("mixed_k30", 11, 30, contig_names=names, fastq_mutator=mutate, n_barcodes=120, ppb=60, mol_len=9000, mols=1)
@@ -237,6 +256,7 @@ def main():
     run_ref(d, ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], "a")
     add_dist_cases()
     make_sam_case()
+    add_shuffled_case()
     print("fixtures written under", OUT)
     subprocess.call(["du", "-sh", OUT])
 
