@@ -314,7 +314,13 @@ def main():
     n_contigs = len(iv) // 2
 
     idx = arcs_b200.ArksIndex(K, int(h_end_off[-1]), device=local)
-    stream = torch.cuda.current_stream()
+    # the kernels must run on the stream the CUDA events are recorded on: a real (non-default) torch stream,
+    # made current so that the workload generation, the events and the library all use it (a null stream
+    # handle would make the library fall back to its own stream, which torch's events do not see)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.current_stream().synchronize()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     idx.set_stream(stream.cuda_stream)
     t0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -363,12 +369,18 @@ def main():
         clocks.start()
     launches0 = idx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1000
     ms = e0.elapsed_time(e1)
+    # the events bracket the kernels on their own stream; the host clock around the same region (which ends
+    # with a synchronize) can only be longer -- if it is much longer the events missed the work
+    if ms < 0.5 * wall_ms - 1.0:
+        raise SystemExit("bench.py: CUDA events (%.3f ms) do not cover the timed region (%.3f ms wall)" % (ms, wall_ms))
     gpu_launches = idx.launches - launches0
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
