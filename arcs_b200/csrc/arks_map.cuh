@@ -905,7 +905,14 @@ struct GroupSmem
 };
 static_assert(sizeof(GroupSmem::Scratch::Lists) <= sizeof(GroupSmem::Scratch::Masks), "lookup lists must fit in the mask rows");
 
-constexpr uint32_t kChunkWindows = 8; // consecutive windows one lane looks up with a rolling key
+#ifndef ARKS_MM_UNROLL
+#define ARKS_MM_UNROLL 1
+#endif
+constexpr int kMismatchUnroll = ARKS_MM_UNROLL; // unroll factor of the read-vs-text comparison loop
+#ifndef ARKS_CHUNK
+#define ARKS_CHUNK 8
+#endif
+constexpr uint32_t kChunkWindows = ARKS_CHUNK; // consecutive windows (<= 8) one lane looks up with a rolling key
 #ifndef ARKS_LOOKUP_BATCH
 #define ARKS_LOOKUP_BATCH 1
 #endif
@@ -1081,13 +1088,26 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 		G.nbad[lane] = 0;
 		const uint32_t total_words = __shfl_sync(0xFFFFFFFFu, incl, 31);
 		__syncwarp();
+#ifndef ARKS_NO_FAST_DIV
+		// all 32 reads need the same number of words (the usual case): read index by multiplication
+		const uint32_t nw0 = __shfl_sync(0xFFFFFFFFu, nwords, 0);
+		const bool uniform = nw0 != 0 && __all_sync(0xFFFFFFFFu, nwords == nw0);
+		const uint32_t magic = nw0 ? 0xFFFFFFFFu / nw0 + 1u : 0u;
+#endif
 		for (uint32_t f = lane; f < total_words; f += 32) {
 			// read r with woff[r] <= f < woff[r+1]
 			uint32_t r = 0;
+#ifndef ARKS_NO_FAST_DIV
+			if (uniform) {
+				r = __umulhi(f, magic);
+			} else
+#endif
+			{
 #pragma unroll
-			for (int step = 16; step > 0; step >>= 1)
-				if (G.woff[r + step] <= f)
-					r += step;
+				for (int step = 16; step > 0; step >>= 1)
+					if (G.woff[r + step] <= f)
+						r += step;
+			}
 			const uint32_t j = f - G.woff[r];
 			const uint32_t roff = P.read_off[2 * pair0 + r];
 			const uint32_t rlen = P.read_off[2 * pair0 + r + 1] - roff;
@@ -1210,7 +1230,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 						for (uint32_t i = 0; i <= nmw; ++i)
 							Bm[i] = 0u;
 						uint32_t any_mm = 0;
-#pragma unroll 1
+#pragma unroll kMismatchUnroll
 						for (uint32_t j = 0; j < nw; ++j) {
 							const uint32_t sw = same ? Wr[j] : rev2(~Wr[nw - 1 - j]);
 							uint32_t m16 = mismatch16(sw, P.ct_T, D + 16 * (int64_t)j, (int64_t)P.ct_n_bases);
