@@ -4,18 +4,20 @@
 // checkReadSequence (:366-389) on both mates, bestContig (:939-1014) on both mates,
 // and imap[barcode][contigRecord[c]]++ (:1280-1285).
 //
-// One warp per read pair.  The warp packs both mates to 2 bits in its private slice of
-// shared memory (forward + reverse-complement streams + invalid-base mask); every lane
-// then owns independent windows: it extracts the canonical key with funnel shifts
-// (no rolling state), hashes it and probes the frozen table with one 16/32-byte
-// non-allocating load.  Four probes per lane are in flight before the first is
-// consumed.  Because a random probe costs a whole 128-byte DRAM line on this chip
-// (profiles/r01_probe_microbench.txt), only a few seed windows per mate are probed first;
-// a seed hit locates the read in the packed contig text and every window that matches the
-// text exactly is resolved by comparison (seed-and-extend) -- the remaining windows are
-// probed.  Per-read votes live in registers, one tracked contig end per lane; the
-// argmax (ties -> smallest contig end, as std::map iteration with a strict '<' gives,
-// :996-1004) and the Jaccard gate (IEEE double division, :1006) finish in the warp.
+// Two kernels per batch:
+//  * map_groups_kernel -- a warp takes 16 pairs = 32 reads: packs them to 2 bits, then ONE LANE PER READ
+//    probes a few seed windows, compares the read with the packed contig text along the seed's
+//    diagonal and classifies every window word-parallel (found iff the text window was inserted,
+//    recorded iff its key is unique); the windows that still have to be looked up (they overlap a
+//    sequencing error) are dealt flat over the warp in chunks with a rolling key, go through an
+//    L2-resident membership filter first, and reach the table only on a filter positive.
+//  * map_slow_kernel -- the general warp-per-pair path (per-window test, compacted probe list, votes for
+//    up to 32 contig ends in registers) for the pairs the first kernel hands over: no seed hit, votes
+//    for three contig ends, reads longer than 256 bases.
+// map_pairs_kernel (warp per pair for every pair) is kept as an independent implementation for A/B
+// runs and tests/test_gpu_properties.py.  The argmax (ties -> smallest contig end, as std::map
+// iteration with a strict '<' gives, :996-1004) and the Jaccard gate (:1006) are exact: the gate is a
+// host-built integer table of the reference's double-precision expression.
 #pragma once
 #include "arks_device.cuh"
 #include <cstdio>
