@@ -24,12 +24,16 @@ def main():
     ap.add_argument("--genome", type=int, default=10_000_000)
     ap.add_argument("--pairs", type=int, default=2_000_000)
     ap.add_argument("--keep", default=None)
+    ap.add_argument("--gz", action="store_true", help="feed both programs the gzip-compressed FASTQ (single-stream zlib inflate on both sides)")
     args = ap.parse_args()
     threads = os.cpu_count() or 1
     tmp = args.keep or tempfile.mkdtemp(prefix="arks_wall_")
     os.makedirs(tmp, exist_ok=True)
     t0 = time.time()
     fa, fq, mult, windows = bench.write_cpu_sample(np, tmp, args.genome, args.pairs, 7)
+    if args.gz:
+        subprocess.check_call(["gzip", "-1", "-f", fq])
+        fq += ".gz"
     gen_s = time.time() - t0
     common = ["-f", fa, "-k", str(bench.K), "-j", str(bench.J), "-c", "5", "-m", "50-10000", "-e", "30000", "-z", "500", "-r", "0.05"]
     t0 = time.time()
@@ -47,8 +51,8 @@ def main():
 
     log = open(os.path.join(tmp, "gpu.log")).read()
     out = {
-        "workload": "%d Mbp draft + %d read pairs (2x150 bp), k=%d, uncompressed FASTQ %.2f GB" % (
-            args.genome // 1_000_000, args.pairs, bench.K, os.path.getsize(fq) / 1e9),
+        "workload": "%d Mbp draft + %d read pairs (2x150 bp), k=%d, %s FASTQ %.2f GB" % (
+            args.genome // 1_000_000, args.pairs, bench.K, "gzip-compressed" if args.gz else "uncompressed", os.path.getsize(fq) / 1e9),
         "read_kmers": windows, "host_threads": threads,
         "gpu_wall_s": gpu_s, "reference_wall_s": ref_s, "speedup_wall": ref_s / gpu_s,
         "reference_phases": json.load(open(os.path.join(tmp, "ref.json"))),
