@@ -446,8 +446,8 @@ class ParallelIngest
 		m_cfg = cfg;
 		m_opt = opt;
 		m_frozen = frozen;
-		// plain regular files are memory-mapped (blocks are cut in place, nothing is copied); gzip files and
-		// pipes go through zlib (transparent for plain data) into block buffers
+		// plain regular files are memory-mapped (blocks are cut in place, nothing is copied); gzip files (fast
+		// decoder) and pipes (zlib, transparent for plain data) are read into block buffers
 		m_fd = ::open(path.c_str(), O_RDONLY);
 		if (m_fd < 0)
 			return false;
@@ -464,13 +464,11 @@ class ParallelIngest
 			}
 		}
 		if (!m_map) {
-			m_gz = gzdopen(m_fd, "r");
-			if (!m_gz) {
-				::close(m_fd);
-				m_fd = -1;
+			::close(m_fd);
+			m_fd = -1;
+			m_src = open_source(path);
+			if (!m_src)
 				return false;
-			}
-			gzbuffer(m_gz, 1u << 20);
 		}
 		m_bufs.resize(m_opt.slots.size());
 		for (size_t i = 0; i < m_opt.slots.size(); ++i)
@@ -565,10 +563,9 @@ class ParallelIngest
 			munmap((void*)m_map, m_map_size);
 			m_map = nullptr;
 			lseek(m_fd, (off_t)m_map_pos, SEEK_SET);
-			m_gz = gzdopen(m_fd, "r");
+			m_src.reset(new ZlibSource(gzdopen(m_fd, "r")));
 		}
-		SeqReader rd(m_gz, std::move(prefix)); // takes the stream over (and closes it)
-		m_gz = nullptr;
+		SeqReader rd(std::move(m_src), std::move(prefix)); // takes the stream over (and closes it)
 		m_fd = -1;
 		m_finished = true;
 		ingest_sequential(rd, bc, m_cfg, counting, ctr, sink);
@@ -622,7 +619,7 @@ class ParallelIngest
 				const size_t want = carry.size() + m_opt.block_bytes;
 				carry.clear();
 				while (have < want) {
-					const int n = gzread(m_gz, buf.data() + have, (unsigned)std::min<size_t>(want - have, 1u << 30));
+					const long n = m_src->read(buf.data() + have, want - have);
 					if (n <= 0) {
 						eof = true;
 						break;
@@ -707,7 +704,7 @@ class ParallelIngest
 	ParallelIngestOptions m_opt;
 	const Barcodes* m_frozen = nullptr;
 	int m_fd = -1;
-	gzFile m_gz = nullptr;
+	std::unique_ptr<ByteSource> m_src; // gzip files and pipes
 	const char* m_map = nullptr;
 	size_t m_map_size = 0, m_map_pos = 0; // m_map_pos: first byte that has not been cut into a block (reader thread)
 	std::vector<std::vector<char>> m_bufs;

@@ -10,16 +10,108 @@
 //  * '+' starts the quality: skip that line, then append lines until quality is at least as
 //    long as the sequence; a length mismatch is error -2, EOF is -1.
 //
-// Works for plain and gzip input (gzread is transparent for uncompressed files).
+// Works for plain and gzip input, files and pipes (open_source: gzip files on disk through the fast decoder of
+// fast_inflate.h, the rest through zlib, whose gzread passes uncompressed data through).
 #pragma once
+#include "fast_inflate.h"
+
 #include <algorithm>
 #include <cctype>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
+#include <memory>
 #include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <vector>
 #include <zlib.h>
 
 namespace arks_host {
+
+// ---- where the bytes come from -------------------------------------------------------------------
+struct ByteSource
+{
+	virtual ~ByteSource() {}
+	virtual long read(char* dst, size_t n) = 0; // <= 0: end of the stream
+};
+
+// zlib: gzip or plain, files and pipes
+struct ZlibSource : ByteSource
+{
+	gzFile fp;
+	explicit ZlibSource(gzFile f)
+	  : fp(f)
+	{
+	}
+	~ZlibSource() override
+	{
+		if (fp)
+			gzclose(fp);
+	}
+	long read(char* dst, size_t n) override { return fp ? gzread(fp, dst, (unsigned)std::min<size_t>(n, 1u << 30)) : 0; }
+};
+
+// a gzip file on disk through fast_inflate.h (memory-mapped)
+struct FastGzSource : ByteSource
+{
+	std::string path;
+	const uint8_t* map;
+	size_t size;
+	std::unique_ptr<FastInflate> inf;
+	bool warned = false;
+	FastGzSource(const std::string& p, const uint8_t* m, size_t n)
+	  : path(p)
+	  , map(m)
+	  , size(n)
+	  , inf(new FastInflate(m, n))
+	{
+	}
+	~FastGzSource() override
+	{
+		inf.reset();
+		munmap((void*)map, size);
+	}
+	long read(char* dst, size_t n) override
+	{
+		const long got = inf->read(dst, n);
+		if (!inf->ok() && !warned) {
+			// like a gzread error upstream, a damaged file ends the input where the damage is -- but not silently
+			fprintf(stderr, "arcs: warning: %s: gzip stream ends early: %s\n", path.c_str(), inf->error().c_str());
+			warned = true;
+		}
+		return got;
+	}
+};
+
+// Opens `path` for reading: gzip files on disk get the fast decoder (ARKS_ZLIB=1: always zlib), everything
+// else (plain files, pipes) goes through zlib, which passes plain data through.  Null if it cannot be opened.
+inline std::unique_ptr<ByteSource> open_source(const std::string& path)
+{
+	const int fd = ::open(path.c_str(), O_RDONLY);
+	if (fd < 0)
+		return nullptr;
+	struct stat st;
+	unsigned char magic[2] = { 0, 0 };
+	const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 18;
+	if (regular && !getenv("ARKS_ZLIB") && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+		void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+		if (m != MAP_FAILED) {
+			madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+			::close(fd);
+			return std::unique_ptr<ByteSource>(new FastGzSource(path, (const uint8_t*)m, (size_t)st.st_size));
+		}
+	}
+	gzFile fp = gzdopen(fd, "r");
+	if (!fp) {
+		::close(fd);
+		return nullptr;
+	}
+	gzbuffer(fp, 1u << 18);
+	return std::unique_ptr<ByteSource>(new ZlibSource(fp));
+}
 
 struct SeqRecord
 {
@@ -41,29 +133,23 @@ class SeqReader
 {
   public:
 	explicit SeqReader(const std::string& path, size_t bufsize = 1u << 20)
-	  : m_buf(bufsize)
+	  : m_src(open_source(path))
+	  , m_buf(bufsize)
 	{
-		m_fp = gzopen(path.c_str(), "r");
-		if (m_fp)
-			gzbuffer(m_fp, 1u << 18);
+		m_opened = m_src != nullptr;
 	}
 	// continues an already open stream: `prefix` (bytes that were read ahead of it) comes first.
-	// Takes ownership of fp (which may be null: then only the prefix is read).
-	SeqReader(gzFile fp, std::string prefix, size_t bufsize = 1u << 20)
-	  : m_fp(fp)
+	// `src` may be null: then only the prefix is read.
+	SeqReader(std::unique_ptr<ByteSource> src, std::string prefix, size_t bufsize = 1u << 20)
+	  : m_src(std::move(src))
 	  , m_buf(bufsize)
 	  , m_prefix(std::move(prefix))
 	  , m_opened(true)
 	{
 	}
-	~SeqReader()
-	{
-		if (m_fp)
-			gzclose(m_fp);
-	}
 	SeqReader(const SeqReader&) = delete;
 	SeqReader& operator=(const SeqReader&) = delete;
-	bool ok() const { return m_fp != nullptr || m_opened; }
+	bool ok() const { return m_opened; }
 
 	// >= 0: sequence length; -1: end of file; -2: truncated / mismatched quality
 	int read(SeqRecord& r)
@@ -121,7 +207,7 @@ class SeqReader
 				std::string().swap(m_prefix), m_prefix_pos = 0;
 			return true;
 		}
-		int n = m_fp ? gzread(m_fp, m_buf.data(), (unsigned)m_buf.size()) : 0;
+		const long n = m_src ? m_src->read(m_buf.data(), m_buf.size()) : 0;
 		m_end = n > 0 ? (size_t)n : 0;
 		if (m_end == 0) {
 			m_eof = true;
@@ -183,7 +269,7 @@ class SeqReader
 		return true;
 	}
 
-	gzFile m_fp = nullptr;
+	std::unique_ptr<ByteSource> m_src;
 	std::vector<char> m_buf;
 	std::string m_prefix;
 	size_t m_prefix_pos = 0;

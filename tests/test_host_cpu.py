@@ -280,3 +280,113 @@ def test_parse_bx_tag_known_answers():
         assert out.split(b"\n")[0] == b"P\tCGTCAGGTCAGAGGTG-1\tACGT\tACGT"
         assert b"emptybarcode=1" in out
         assert _ingest("par", fq, 2, 64)[0] == out
+
+
+# ---- fast_inflate.h (the gzip decoder of the read ingest) against zlib ------------------------------------
+INFLATE = os.path.join(ROOT, "arcs_b200", "bin", "inflate_check")
+
+
+def _build_inflate():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "arcs_b200", "host"), "../bin/inflate_check"])
+
+
+def _fast_inflate(path, chunk=1 << 20):
+    p = subprocess.run([INFLATE, "fast", str(path), str(chunk)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    err = [ln for ln in p.stderr.decode().splitlines() if ln.startswith("ERROR")]
+    return p.stdout, (err[0] if err else None)
+
+
+def _gz(data, level=6, strategy=0, mem_level=8):
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, 31, mem_level, strategy)
+    return c.compress(data) + c.flush()
+
+
+def _payloads():
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    fastq = b"".join(b"@r%d BX:Z:ACGTACGTAC-1\n%s\n+\n%s\n" % (i, acgt[rng.integers(0, 4, 150)].tobytes(),
+                                                          bytes(rng.integers(35, 75, 150, dtype=np.uint8))) for i in range(4000))
+    far = bytes(rng.integers(0, 256, 32768, dtype=np.uint8))
+    return {
+        "empty": b"",
+        "one_byte": b"x",
+        "fastq": fastq,
+        "random_bytes": bytes(rng.integers(0, 256, 300_000, dtype=np.uint8)),
+        "runs": b"A" * 100_000 + b"AB" * 50_000 + b"ABC" * 40_000 + b"ABCDEFG" * 20_000,
+        "window_edge": (far + b"-" + far[:20000] + far[1:] + b"+" + far) * 3,  # matches at distance 32768 and 32767
+        "text": b" ".join(b"w%d" % (i * 7919 % 1000) for i in range(200_000)),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_payloads()))
+def test_fast_inflate_matches_zlib_on_every_block_type(name, tmp_path):
+    import zlib
+    _build_inflate()
+    data = _payloads()[name]
+    variants = [(lv, 0, 8) for lv in (0, 1, 4, 6, 9)] + [(6, zlib.Z_FIXED, 8), (6, zlib.Z_HUFFMAN_ONLY, 8), (6, zlib.Z_RLE, 8),
+                                                           (6, zlib.Z_FILTERED, 8), (9, 0, 1), (1, 0, 9)]
+    for i, (lv, strat, ml) in enumerate(variants):
+        path = tmp_path / ("v%d.gz" % i)
+        path.write_bytes(_gz(data, lv, strat, ml))
+        out, err = _fast_inflate(path, chunk=(1 << 20) if i % 2 else 4099)
+        assert err is None, (name, lv, strat, err)
+        assert out == data, (name, lv, strat)
+
+
+def test_fast_inflate_members_headers_and_chunk_sizes(tmp_path):
+    import struct
+    import zlib
+    _build_inflate()
+    p = _payloads()
+    # several members, an empty one among them, then trailing zeros (ignored like zlib does)
+    blob = _gz(p["fastq"][:50000]) + _gz(b"") + _gz(p["text"][:70001], 9) + _gz(p["runs"], 1)
+    want = p["fastq"][:50000] + p["text"][:70001] + p["runs"]
+    (tmp_path / "multi.gz").write_bytes(blob + b"\0" * 37)
+    for chunk in (1, 7, 4096, 1 << 20):
+        if chunk == 1 and len(want) > 300000:
+            continue
+        out, err = _fast_inflate(tmp_path / "multi.gz", chunk)
+        assert err is None and out == want
+    # header with FEXTRA, FNAME, FCOMMENT and FHCRC
+    raw = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = raw.compress(p["text"]) + raw.flush()
+    hdr = b"\x1f\x8b\x08" + bytes([4 | 8 | 16 | 2]) + b"\0\0\0\0\x00\x03" + struct.pack("<H", 5) + b"EXTRA" + b"name.fq\0" + b"a comment\0"
+    hdr += struct.pack("<H", zlib.crc32(hdr) & 0xFFFF)
+    (tmp_path / "flags.gz").write_bytes(hdr + body + struct.pack("<II", zlib.crc32(p["text"]), len(p["text"]) & 0xFFFFFFFF))
+    out, err = _fast_inflate(tmp_path / "flags.gz")
+    assert err is None and out == p["text"]
+    # an empty file is an empty stream; a file that is not gzip is an error
+    (tmp_path / "empty.gz").write_bytes(b"")
+    assert _fast_inflate(tmp_path / "empty.gz") == (b"", None)
+    (tmp_path / "plain.gz").write_bytes(b"@r1\nACGT\n+\nIIII\n" * 10)
+    out, err = _fast_inflate(tmp_path / "plain.gz")
+    assert out == b"" and err is not None
+
+
+def test_fast_inflate_reports_truncation_and_corruption(tmp_path):
+    _build_inflate()
+    data = _payloads()["fastq"]
+    blob = _gz(data)
+    for cut in (len(blob) - 1, len(blob) - 8, len(blob) - 9, len(blob) // 2, 40, 12, 5):
+        (tmp_path / "t.gz").write_bytes(blob[:cut])
+        out, err = _fast_inflate(tmp_path / "t.gz")
+        assert err is not None, cut
+        assert data.startswith(out)  # everything handed out before the defect is right
+    rng = np.random.default_rng(11)
+    detected = 0
+    for t in range(40):
+        b = bytearray(blob)
+        pos = int(rng.integers(20, len(b) - 8))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        (tmp_path / "c.gz").write_bytes(bytes(b))
+        out, err = _fast_inflate(tmp_path / "c.gz")
+        detected += err is not None
+        assert err is not None or out == data  # a flipped bit is either caught (structure / CRC-32 / length) or harmless
+    assert detected >= 38
+    # wrong CRC and wrong ISIZE in the trailer
+    for off in (-8, -4):
+        b = bytearray(blob)
+        b[off] ^= 0x55
+        (tmp_path / "c.gz").write_bytes(bytes(b))
+        assert _fast_inflate(tmp_path / "c.gz")[1] is not None
