@@ -36,6 +36,33 @@ class FastInflate
 			w.resize(kHist + kOutCap + kSlack);
 		m_crc_thread = std::thread([this] { crc_loop(); });
 	}
+	// continues a member in the middle: `bitpos` is the position of a block header, `window` the 32 KB of
+	// output in front of it, `crc` / `member_out` the CRC-32 and length of the member's output so far
+	FastInflate(const uint8_t* in, size_t n, uint64_t bitpos, const uint8_t* window, uint32_t crc, uint64_t member_out)
+	  : m_ip(in + (size_t)(bitpos >> 3))
+	  , m_in_end(in + n)
+	{
+		for (auto& w : m_wins)
+			w.resize(kHist + kOutCap + kSlack);
+		memcpy(m_wins[0].data(), window, kHist);
+		refill();
+		bits((int)(bitpos & 7));
+		m_state = S_BLOCK_HEADER;
+		m_total_out = kHist; // the whole window may be referenced
+		m_crc = crc;
+		m_member_out = member_out;
+		m_members = 1;
+		m_crc_thread = std::thread([this] { crc_loop(); });
+	}
+	// what follows a complete member: further members, or trailing bytes that are ignored
+	struct AfterMember
+	{
+	};
+	FastInflate(const uint8_t* in, size_t n, AfterMember)
+	  : FastInflate(in, n)
+	{
+		m_members = 1;
+	}
 	~FastInflate()
 	{
 		{

@@ -390,3 +390,78 @@ def test_fast_inflate_reports_truncation_and_corruption(tmp_path):
         b[off] ^= 0x55
         (tmp_path / "c.gz").write_bytes(bytes(b))
         assert _fast_inflate(tmp_path / "c.gz")[1] is not None
+
+
+# ---- par_inflate.h (multi-threaded decoding of one gzip member) against the data and against zlib ----------
+def _par_inflate(path, threads=4, par_chunk=1 << 16, chunk=1 << 20):
+    p = subprocess.run([INFLATE, "par%d" % threads, str(path), str(chunk)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True,
+                       env=dict(os.environ, PAR_CHUNK=str(par_chunk)))
+    lines = p.stderr.decode().splitlines()
+    err = [ln for ln in lines if ln.startswith("ERROR")]
+    nchunks = [int(ln.split()[1]) for ln in lines if ln.startswith("PARALLEL_CHUNKS")]
+    return p.stdout, (err[0] if err else None), (nchunks[0] if nchunks else 0)
+
+
+def _big_fastq(n_reads, seed):
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    recs = []
+    for i in range(n_reads):
+        L = int(rng.integers(100, 151))
+        recs.append(b"@read%d/%d BX:Z:%s-1\n%s\n+\n%s\n" % (i // 2, i % 2 + 1, acgt[rng.integers(0, 4, 16)].tobytes(),
+                                                           acgt[rng.integers(0, 5, L) % 4].tobytes(), bytes(rng.integers(35, 75, L, dtype=np.uint8))))
+    return b"".join(recs)
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_par_inflate_fastq(level, threads, tmp_path):
+    _build_inflate()
+    data = _big_fastq(30000, level * 10 + threads)  # ~10 MB
+    path = tmp_path / "r.fq.gz"
+    path.write_bytes(_gz(data, level))
+    out, err, nchunks = _par_inflate(path, threads, par_chunk=1 << 17)
+    assert err is None and out == data
+    assert nchunks >= 8  # the chunks really were decoded independently
+    out, err, _ = _par_inflate(path, threads, par_chunk=1 << 16, chunk=4099)
+    assert err is None and out == data
+
+
+@pytest.mark.parametrize("name", sorted(_payloads()))
+def test_par_inflate_any_payload(name, tmp_path):
+    """whatever the data (binary data has no findable block starts, runs and far matches stress the window
+    symbols), the result is the sequential one"""
+    import zlib
+    _build_inflate()
+    data = _payloads()[name]
+    for i, (lv, strat) in enumerate([(1, 0), (6, 0), (9, 0), (0, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)]):
+        path = tmp_path / ("v%d.gz" % i)
+        path.write_bytes(_gz(data, lv, strat))
+        out, err, _ = _par_inflate(path, 4, par_chunk=1 << 16)
+        assert err is None, (name, lv, strat, err)
+        assert out == data, (name, lv, strat)
+
+
+def test_par_inflate_members_garbage_truncation_corruption(tmp_path):
+    _build_inflate()
+    a, b = _big_fastq(8000, 1), _big_fastq(3000, 2)
+    # a second member and trailing zeros behind the first: the first goes parallel, the rest sequentially
+    (tmp_path / "m.gz").write_bytes(_gz(a, 6) + _gz(b, 1) + b"\0" * 11)
+    out, err, nchunks = _par_inflate(tmp_path / "m.gz", 4)
+    assert err is None and out == a + b and nchunks > 4
+    (tmp_path / "g.gz").write_bytes(_gz(a, 6) + b"\0" * 100)
+    out, err, _ = _par_inflate(tmp_path / "g.gz", 4)
+    assert err is None and out == a
+    blob = _gz(a, 6)
+    for cut in (len(blob) - 1, len(blob) - 9, len(blob) // 2, len(blob) // 3, 40):
+        (tmp_path / "t.gz").write_bytes(blob[:cut])
+        out, err, _ = _par_inflate(tmp_path / "t.gz", 4)
+        assert err is not None, cut
+        assert a.startswith(out), cut
+    rng = np.random.default_rng(4)
+    for t in range(30):
+        c = bytearray(blob)
+        c[int(rng.integers(20, len(c) - 8))] ^= 1 << int(rng.integers(0, 8))
+        (tmp_path / "c.gz").write_bytes(bytes(c))
+        out, err, _ = _par_inflate(tmp_path / "c.gz", 4)
+        assert err is not None or out == a
