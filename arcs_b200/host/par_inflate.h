@@ -371,7 +371,21 @@ class ParInflate
 	{
 		if (!parse_header())
 			start_sequential_from_scratch();
+		else
+			m_producer = std::thread([this] { producer_loop(); });
 	}
+	~ParInflate()
+	{
+		{
+			std::lock_guard<std::mutex> lk(m_mu);
+			m_quit = true;
+		}
+		m_cv.notify_all();
+		if (m_producer.joinable())
+			m_producer.join();
+	}
+	ParInflate(const ParInflate&) = delete;
+	ParInflate& operator=(const ParInflate&) = delete;
 	bool ok() const { return m_err.empty() && (!m_seq || m_seq->ok()); }
 	std::string error() const { return !m_err.empty() ? m_err : (m_seq ? m_seq->error() : std::string()); }
 	size_t parallel_chunks() const { return m_par_chunks; }
@@ -380,18 +394,38 @@ class ParInflate
 	{
 		size_t got = 0;
 		while (got < n) {
-			if (m_serve < m_good) { // what the last wave produced goes out first, chunk after chunk
-				const std::vector<uint8_t>& b = m_chunks[m_serve].bytes;
-				const size_t c = std::min(n - got, b.size() - m_rpos);
-				memcpy(dst + got, b.data() + m_rpos, c);
-				m_rpos += c;
-				got += c;
-				if (m_rpos == b.size()) {
-					m_serve++;
-					m_rpos = 0;
+			if (m_cur) { // a finished wave: its chunks go out one after the other
+				if (m_serve < m_cur->good) {
+					const std::vector<uint8_t>& b = m_cur->chunks[m_serve].bytes;
+					const size_t c = std::min(n - got, b.size() - m_rpos);
+					memcpy(dst + got, b.data() + m_rpos, c);
+					m_rpos += c;
+					got += c;
+					if (m_rpos == b.size()) {
+						m_serve++;
+						m_rpos = 0;
+					}
+					continue;
 				}
-				continue;
+				{ // hand the buffers back to the producer
+					std::lock_guard<std::mutex> lk(m_mu);
+					m_cur->ready = false;
+				}
+				m_cv.notify_all();
+				m_cur = nullptr;
+				m_cons ^= 1;
 			}
+			if (m_producer.joinable()) {
+				std::unique_lock<std::mutex> lk(m_mu);
+				m_cv.wait(lk, [&] { return m_out[m_cons].ready || m_producer_done; });
+				if (m_out[m_cons].ready) {
+					m_cur = &m_out[m_cons];
+					m_serve = 0;
+					m_rpos = 0;
+					continue;
+				}
+			}
+			// the producer has stopped: error, end of the member, or the sequential decoder takes over
 			if (!m_err.empty())
 				break;
 			if (m_seq) {
@@ -401,9 +435,7 @@ class ParInflate
 				got += (size_t)r;
 				continue;
 			}
-			if (m_done)
-				break;
-			wave();
+			break;
 		}
 		return (long)got;
 	}
@@ -462,10 +494,45 @@ class ParInflate
 	};
 
 	// one wave: up to m_threads chunks found, decoded, resolved and queued for read()
-	void wave()
+	struct WaveOut
 	{
-		m_serve = m_good = 0;
-		m_rpos = 0;
+		std::vector<Chunk> chunks; // (objects and buffers are reused from wave to wave)
+		size_t good = 0;           // number of chunks that held up, in order
+		bool ready = false;        // filled, waiting for read()
+	};
+
+	// waves are produced ahead of read() on a thread of their own, into two alternating sets of buffers
+	void producer_loop()
+	{
+		int slot = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> lk(m_mu);
+				m_cv.wait(lk, [&] { return m_quit || !m_out[slot].ready; });
+				if (m_quit)
+					break;
+			}
+			wave(m_out[slot]);
+			const bool stop = m_done || m_seq || !m_err.empty();
+			{
+				std::lock_guard<std::mutex> lk(m_mu);
+				m_out[slot].ready = m_out[slot].good > 0;
+				if (stop)
+					m_producer_done = true;
+			}
+			m_cv.notify_all();
+			if (stop)
+				break;
+			slot ^= 1;
+		}
+		std::lock_guard<std::mutex> lk(m_mu);
+		m_producer_done = true;
+		m_cv.notify_all();
+	}
+
+	void wave(WaveOut& W)
+	{
+		W.good = 0;
 		const uint64_t data_end = (uint64_t)(m_n - 8) * 8; // the trailer starts here at the latest
 		// 1. chunk starts: the first is the validated position m_pos, the others are hunted for in parallel
 		const int want = m_threads;
@@ -484,8 +551,7 @@ class ParInflate
 		}
 		// chunks = stretches between consecutive starts that were found (a missing one merges two chunks); the last
 		// chunk of the wave simply stops at the first block boundary behind its share of the input
-		// (the Chunk objects and their buffers are reused from wave to wave)
-		std::vector<Chunk>& chunks = m_chunks;
+		std::vector<Chunk>& chunks = W.chunks;
 		if (chunks.size() < (size_t)want)
 			chunks.resize((size_t)want);
 		size_t n_chunks = 0;
@@ -581,7 +647,7 @@ class ParInflate
 			for (auto& t : th)
 				t.join();
 		}
-		m_good = good;
+		W.good = good;
 		for (size_t i = 0; i < good; ++i) {
 			Chunk& c = chunks[i];
 			m_crc = (uint32_t)crc32_combine(m_crc, c.crc, (z_off_t)c.bytes.size());
@@ -589,7 +655,7 @@ class ParInflate
 			m_pos = c.end;
 			m_par_chunks++;
 			if (c.final) {
-				m_good = i + 1;
+				W.good = i + 1;
 				finish_member();
 				return;
 			}
@@ -630,9 +696,14 @@ class ParInflate
 	std::vector<uint8_t> m_window = std::vector<uint8_t>(32768, 0);
 	uint32_t m_crc = 0;
 	uint64_t m_out_total = 0;
-	std::vector<Chunk> m_chunks;
-	size_t m_serve = 0, m_good = 0; // chunks of the last wave: next to hand out, number that held up
-	size_t m_rpos = 0, m_par_chunks = 0;
+	WaveOut m_out[2];
+	WaveOut* m_cur = nullptr; // the wave read() is handing out
+	int m_cons = 0;           // the set read() takes next
+	size_t m_serve = 0, m_rpos = 0, m_par_chunks = 0;
+	std::thread m_producer;
+	std::mutex m_mu;
+	std::condition_variable m_cv;
+	bool m_quit = false, m_producer_done = false;
 	std::unique_ptr<FastInflate> m_seq;
 	std::string m_err;
 };

@@ -13,7 +13,7 @@
 // Works for plain and gzip input, files and pipes (open_source: gzip files on disk through the fast decoder of
 // fast_inflate.h, the rest through zlib, whose gzread passes uncompressed data through).
 #pragma once
-#include "fast_inflate.h"
+#include "par_inflate.h"
 
 #include <algorithm>
 #include <cctype>
@@ -54,37 +54,55 @@ struct ZlibSource : ByteSource
 	long read(char* dst, size_t n) override { return fp ? gzread(fp, dst, (unsigned)std::min<size_t>(n, 1u << 30)) : 0; }
 };
 
-// a gzip file on disk through fast_inflate.h (memory-mapped)
+// a gzip file on disk (memory-mapped) through fast_inflate.h, or, when it is large and threads are to be had,
+// through the multi-threaded decoder of par_inflate.h
 struct FastGzSource : ByteSource
 {
 	std::string path;
 	const uint8_t* map;
 	size_t size;
 	std::unique_ptr<FastInflate> inf;
+	std::unique_ptr<ParInflate> par;
 	bool warned = false;
-	FastGzSource(const std::string& p, const uint8_t* m, size_t n)
+	FastGzSource(const std::string& p, const uint8_t* m, size_t n, int threads)
 	  : path(p)
 	  , map(m)
 	  , size(n)
-	  , inf(new FastInflate(m, n))
 	{
+		if (threads > 1)
+			par.reset(new ParInflate(m, n, threads));
+		else
+			inf.reset(new FastInflate(m, n));
 	}
 	~FastGzSource() override
 	{
 		inf.reset();
+		par.reset();
 		munmap((void*)map, size);
 	}
 	long read(char* dst, size_t n) override
 	{
-		const long got = inf->read(dst, n);
-		if (!inf->ok() && !warned) {
+		const long got = par ? par->read(dst, n) : inf->read(dst, n);
+		if (!(par ? par->ok() : inf->ok()) && !warned) {
 			// like a gzread error upstream, a damaged file ends the input where the damage is -- but not silently
-			fprintf(stderr, "arcs: warning: %s: gzip stream ends early: %s\n", path.c_str(), inf->error().c_str());
+			fprintf(stderr, "arcs: warning: %s: gzip stream ends early: %s\n", path.c_str(), (par ? par->error() : inf->error()).c_str());
 			warned = true;
 		}
 		return got;
 	}
 };
+
+// decoder threads for a gzip file of `bytes` compressed bytes: ARKS_GZ_THREADS, else up to 8 (half the cores) for
+// files of at least 8 MB; small files are not worth the threads
+inline int gz_threads_for(size_t bytes)
+{
+	if (const char* e = getenv("ARKS_GZ_THREADS"))
+		return std::max(1, atoi(e));
+	if (bytes < (8u << 20))
+		return 1;
+	const unsigned hw = std::thread::hardware_concurrency();
+	return (int)std::min(8u, std::max(1u, hw / 2));
+}
 
 // Opens `path` for reading: gzip files on disk get the fast decoder (ARKS_ZLIB=1: always zlib), everything
 // else (plain files, pipes) goes through zlib, which passes plain data through.  Null if it cannot be opened.
@@ -101,7 +119,7 @@ inline std::unique_ptr<ByteSource> open_source(const std::string& path)
 		if (m != MAP_FAILED) {
 			madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
 			::close(fd);
-			return std::unique_ptr<ByteSource>(new FastGzSource(path, (const uint8_t*)m, (size_t)st.st_size));
+			return std::unique_ptr<ByteSource>(new FastGzSource(path, (const uint8_t*)m, (size_t)st.st_size, gz_threads_for((size_t)st.st_size)));
 		}
 	}
 	gzFile fp = gzdopen(fd, "r");
