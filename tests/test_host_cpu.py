@@ -465,3 +465,20 @@ def test_par_inflate_members_garbage_truncation_corruption(tmp_path):
         (tmp_path / "c.gz").write_bytes(bytes(c))
         out, err, _ = _par_inflate(tmp_path / "c.gz", 4)
         assert err is not None or out == a
+
+
+def test_ingest_through_the_parallel_gzip_decoder(tmp_path):
+    """the whole read ingest (block-parallel parser) behind the multi-threaded gzip decoder gives the pairs,
+    counters and multiplicities of the sequential reader behind zlib"""
+    _build_ingest()
+    rng = np.random.default_rng(31)
+    data = _strict_fastq(rng, 12000, barcodes=40, tweak=_tweak_pairing)  # ~4 MB of FASTQ
+    path = tmp_path / "reads.fq.gz"
+    with gzip.open(path, "wb", compresslevel=4) as f:
+        f.write(data)
+    ref = subprocess.run([INGEST, "seq", str(path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True,
+                         env=dict(os.environ, ARKS_ZLIB="1")).stdout
+    for threads in ("1", "3", "8"):
+        got = subprocess.run([INGEST, "par", str(path), "4", str(1 << 18)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True,
+                             env=dict(os.environ, ARKS_GZ_THREADS=threads)).stdout
+        assert got == ref, threads
