@@ -21,8 +21,10 @@
 #include "fast_inflate.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <functional>
 #include <memory>
+#include <new>
 #include <thread>
 
 namespace arks_host {
@@ -179,6 +181,34 @@ struct Tables
 	}
 };
 
+// grow-only buffer of 16-bit symbols whose new part is NOT cleared (a std::vector would zero-fill it)
+struct SymBuf
+{
+	uint16_t* p = nullptr;
+	size_t cap = 0;
+	SymBuf() = default;
+	SymBuf(const SymBuf&) = delete;
+	SymBuf& operator=(const SymBuf&) = delete;
+	SymBuf(SymBuf&& o) noexcept
+	  : p(o.p)
+	  , cap(o.cap)
+	{
+		o.p = nullptr;
+		o.cap = 0;
+	}
+	~SymBuf() { free(p); }
+	void ensure(size_t n)
+	{
+		if (n <= cap)
+			return;
+		void* q = realloc(p, n * sizeof(uint16_t));
+		if (!q)
+			throw std::bad_alloc();
+		p = (uint16_t*)q;
+		cap = n;
+	}
+};
+
 inline bool plausible_text(uint32_t c)
 {
 	return c == '\n' || c == '\t' || c == '\r' || (c >= 32 && c < 127);
@@ -189,8 +219,7 @@ inline bool plausible_text(uint32_t c)
 // copy from before it is an error.  `text_only`: every literal must be plausible text (block-start hunting).
 // Returns false on anything invalid; *final tells whether it was the last block of the stream.
 // `out` is used as a buffer: its size is its capacity, `n_out` the number of symbols in it.
-inline bool decode_block(Bits& in, std::vector<uint16_t>& out, size_t& n_out, bool known_start, bool text_only, size_t max_out, bool* final,
-    Tables& T)
+inline bool decode_block(Bits& in, SymBuf& out, size_t& n_out, bool known_start, bool text_only, size_t max_out, bool* final, Tables& T)
 {
 	static const uint16_t lbase[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
 	static const uint8_t lext[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
@@ -208,12 +237,11 @@ inline bool decode_block(Bits& in, std::vector<uint16_t>& out, size_t& n_out, bo
 		const uint32_t len = in.base[b] | (in.base[b + 1] << 8), nlen = in.base[b + 2] | (in.base[b + 3] << 8);
 		if ((len ^ 0xffffu) != nlen || b + 4 + len > in.nbytes)
 			return false;
-		if (out.size() < n_out + len)
-			out.resize(n_out + len + out.size() / 2);
+		out.ensure(n_out + len + (out.cap < n_out + len ? out.cap / 2 : 0));
 		for (uint32_t i = 0; i < len; ++i) {
 			if (text_only && !plausible_text(in.base[b + 4 + i]))
 				return false;
-			out[n_out++] = in.base[b + 4 + i];
+			out.p[n_out++] = in.base[b + 4 + i];
 		}
 		in.pos += (4ull + len) * 8;
 		return true;
@@ -227,10 +255,10 @@ inline bool decode_block(Bits& in, std::vector<uint16_t>& out, size_t& n_out, bo
 	size_t n = start, cap = 0;
 	uint16_t* o = nullptr;
 	auto grow = [&] {
-		if (out.size() < n + (1u << 16) + 300)
-			out.resize(n + (1u << 16) + 300 + out.size() / 2);
-		o = out.data();
-		cap = out.size() - 300;
+		if (out.cap < n + (1u << 16) + 300)
+			out.ensure(n + (1u << 16) + 300 + out.cap / 2);
+		o = out.p;
+		cap = out.cap - 300;
 	};
 	grow();
 	const uint8_t* const base = in.base;
@@ -334,7 +362,7 @@ inline bool decode_block(Bits& in, std::vector<uint16_t>& out, size_t& n_out, bo
 inline uint64_t find_block_start(const uint8_t* base, size_t nbytes, uint64_t from, uint64_t to)
 {
 	Tables T;
-	std::vector<uint16_t> scratch;
+	SymBuf scratch;
 	size_t ns = 0;
 	for (uint64_t p = from; p < to; ++p) {
 		Bits in{ base, nbytes, p };
@@ -363,7 +391,7 @@ inline uint64_t find_block_start(const uint8_t* base, size_t nbytes, uint64_t fr
 class ParInflate
 {
   public:
-	ParInflate(const uint8_t* in, size_t n, int threads, size_t chunk_bytes = 1u << 20)
+	ParInflate(const uint8_t* in, size_t n, int threads, size_t chunk_bytes = 1u << 19)
 	  : m_in(in)
 	  , m_n(n)
 	  , m_threads(std::max(1, threads))
@@ -487,13 +515,29 @@ class ParInflate
 		uint64_t start = 0; // bit position of its first block
 		uint64_t end = 0;   // of the block behind its last one: must be hit exactly (stop_at_any: first boundary >= end)
 		bool stop_at_any = false, known_start = false, ok = false, final = false;
-		std::vector<uint16_t> sym; // buffer ...
+		pinf::SymBuf sym;          // buffer ...
 		size_t n_sym = 0;          // ... and the number of symbols in it
 		std::vector<uint8_t> bytes;
 		uint32_t crc = 0;
 	};
 
 	// one wave: up to m_threads chunks found, decoded, resolved and queued for read()
+	// runs job(i) for i in [0, n) on the decoder threads, handing indices out one at a time
+	template <class F>
+	void run_jobs(size_t n, F job)
+	{
+		std::atomic<size_t> next{ 0 };
+		std::vector<std::thread> th;
+		const size_t nt = std::min<size_t>((size_t)m_threads, n);
+		for (size_t t = 0; t < nt; ++t)
+			th.emplace_back([&] {
+				for (size_t i; (i = next.fetch_add(1)) < n;)
+					job(i);
+			});
+		for (auto& t : th)
+			t.join();
+	}
+
 	struct WaveOut
 	{
 		std::vector<Chunk> chunks; // (objects and buffers are reused from wave to wave)
@@ -535,20 +579,16 @@ class ParInflate
 		W.good = 0;
 		const uint64_t data_end = (uint64_t)(m_n - 8) * 8; // the trailer starts here at the latest
 		// 1. chunk starts: the first is the validated position m_pos, the others are hunted for in parallel
-		const int want = m_threads;
+		// (three chunks per thread and wave, dealt out dynamically, so that a slow chunk does not idle the rest)
+		const int want = 3 * m_threads;
 		std::vector<uint64_t> starts((size_t)want, 0);
 		starts[0] = m_pos;
-		{
-			std::vector<std::thread> th;
-			for (int i = 1; i < want; ++i)
-				th.emplace_back([&, i] {
-					const uint64_t from = ((m_pos >> 3) + (uint64_t)i * m_chunk) * 8;
-					if (from + 64 < data_end)
-						starts[(size_t)i] = pinf::find_block_start(m_in, m_n, from, std::min(data_end, from + (uint64_t)m_chunk * 8));
-				});
-			for (auto& t : th)
-				t.join();
-		}
+		run_jobs((size_t)want - 1, [&](size_t k) {
+			const size_t i = k + 1;
+			const uint64_t from = ((m_pos >> 3) + (uint64_t)i * m_chunk) * 8;
+			if (from + 64 < data_end)
+				starts[i] = pinf::find_block_start(m_in, m_n, from, std::min(data_end, from + (uint64_t)m_chunk * 8));
+		});
 		// chunks = stretches between consecutive starts that were found (a missing one merges two chunks); the last
 		// chunk of the wave simply stops at the first block boundary behind its share of the input
 		std::vector<Chunk>& chunks = W.chunks;
@@ -570,14 +610,11 @@ class ParInflate
 		chunks[n_chunks - 1].stop_at_any = true;
 		// 2. decode every chunk symbolically until its end position (or the final block)
 		{
-			std::vector<std::thread> th;
-			for (size_t ci = 0; ci < n_chunks; ++ci)
-				th.emplace_back([&, ci] {
+			run_jobs(n_chunks, [&](size_t ci) {
 					Chunk& c = chunks[ci];
 					pinf::Tables T;
 					pinf::Bits in{ m_in, m_n, c.start };
-					if (c.sym.size() < m_chunk * 6)
-						c.sym.resize(m_chunk * 6);
+					c.sym.ensure(m_chunk * 6);
 					for (;;) {
 						bool final = false;
 						if (!pinf::decode_block(in, c.sym, c.n_sym, c.known_start, false, 1u << 26, &final, T))
@@ -597,8 +634,6 @@ class ParInflate
 							return;
 					}
 				});
-			for (auto& t : th)
-				t.join();
 		}
 		// 3. resolve in order as far as the chunks hold up; 4. translate + CRC in parallel
 		size_t good = 0;
@@ -615,7 +650,7 @@ class ParInflate
 		windows[0] = m_window;
 		for (size_t i = 0; i < good; ++i) {
 			// window behind chunk i = last 32 K of (window in front of it + its output)
-			const std::vector<uint16_t>& s = chunks[i].sym;
+			const uint16_t* const s = chunks[i].sym.p;
 			const std::vector<uint8_t>& w = windows[i];
 			std::vector<uint8_t>& nw = windows[i + 1];
 			nw.resize(32768);
@@ -632,20 +667,16 @@ class ParInflate
 			}
 		}
 		{
-			std::vector<std::thread> th;
-			for (size_t i = 0; i < good; ++i)
-				th.emplace_back([&, i] {
+			run_jobs(good, [&](size_t i) {
 					Chunk& c = chunks[i];
 					const uint8_t* w = windows[i].data();
 					c.bytes.resize(c.n_sym);
-					const uint16_t* s = c.sym.data();
+					const uint16_t* s = c.sym.p;
 					uint8_t* o = c.bytes.data();
 					for (size_t k = 0, n = c.n_sym; k < n; ++k)
 						o[k] = s[k] < 256 ? (uint8_t)s[k] : w[s[k] - 256];
 					c.crc = (uint32_t)crc32_z(0, o, c.bytes.size());
 				});
-			for (auto& t : th)
-				t.join();
 		}
 		W.good = good;
 		for (size_t i = 0; i < good; ++i) {
