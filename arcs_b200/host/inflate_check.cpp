@@ -1,6 +1,7 @@
 // inflate_check.cpp -- test helper: decompresses a .gz with FastInflate (fast_inflate.h) in reads of a given
 // size and writes the bytes to stdout; prints the error (if any) and the byte count to stderr.  With "zlib"
 // as the first argument it does the same through zlib's gzread, for comparison and timing.
+#include "bgzf_inflate.h"
 #include "par_inflate.h"
 
 #include <chrono>
@@ -47,7 +48,20 @@ int main(int argc, char** argv)
 		struct stat st;
 		fstat(fd, &st);
 		const uint8_t* m = st.st_size ? (const uint8_t*)mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
-		if (parallel) {
+		if (std::string(argv[1]).compare(0, 4, "bgzf") == 0) { // bgzf<threads>
+			const bool is = arks_host::BgzfInflate::is_bgzf(m, (size_t)st.st_size);
+			fprintf(stderr, "IS_BGZF %d\n", (int)is);
+			arks_host::BgzfInflate inf(m, (size_t)st.st_size, argv[1][4] ? atoi(argv[1] + 4) : 4, par_chunk);
+			long n;
+			while ((n = inf.read(buf.data(), chunk)) > 0) {
+				if (!quiet)
+					fwrite(buf.data(), 1, (size_t)n, stdout);
+				total += (size_t)n;
+			}
+			if (!inf.ok())
+				fprintf(stderr, "ERROR %s\n", inf.error().c_str());
+			fprintf(stderr, "PARALLEL_MEMBERS %zu\n", inf.parallel_members());
+		} else if (parallel) {
 			arks_host::ParInflate inf(m, (size_t)st.st_size, par_threads, par_chunk);
 			long n;
 			while ((n = inf.read(buf.data(), chunk)) > 0) {

@@ -13,6 +13,7 @@
 // Works for plain and gzip input, files and pipes (open_source: gzip files on disk through the fast decoder of
 // fast_inflate.h, the rest through zlib, whose gzread passes uncompressed data through).
 #pragma once
+#include "bgzf_inflate.h"
 #include "par_inflate.h"
 
 #include <algorithm>
@@ -55,7 +56,7 @@ struct ZlibSource : ByteSource
 };
 
 // a gzip file on disk (memory-mapped) through fast_inflate.h, or, when it is large and threads are to be had,
-// through the multi-threaded decoder of par_inflate.h
+// through the multi-threaded decoders of par_inflate.h (one DEFLATE stream) or bgzf_inflate.h (bgzip's members)
 struct FastGzSource : ByteSource
 {
 	std::string path;
@@ -63,13 +64,16 @@ struct FastGzSource : ByteSource
 	size_t size;
 	std::unique_ptr<FastInflate> inf;
 	std::unique_ptr<ParInflate> par;
+	std::unique_ptr<BgzfInflate> bgzf;
 	bool warned = false;
 	FastGzSource(const std::string& p, const uint8_t* m, size_t n, int threads)
 	  : path(p)
 	  , map(m)
 	  , size(n)
 	{
-		if (threads > 1)
+		if (threads > 1 && BgzfInflate::is_bgzf(m, n))
+			bgzf.reset(new BgzfInflate(m, n, threads));
+		else if (threads > 1)
 			par.reset(new ParInflate(m, n, threads));
 		else
 			inf.reset(new FastInflate(m, n));
@@ -78,14 +82,16 @@ struct FastGzSource : ByteSource
 	{
 		inf.reset();
 		par.reset();
+		bgzf.reset();
 		munmap((void*)map, size);
 	}
 	long read(char* dst, size_t n) override
 	{
-		const long got = par ? par->read(dst, n) : inf->read(dst, n);
-		if (!(par ? par->ok() : inf->ok()) && !warned) {
+		const long got = bgzf ? bgzf->read(dst, n) : par ? par->read(dst, n) : inf->read(dst, n);
+		if (!(bgzf ? bgzf->ok() : par ? par->ok() : inf->ok()) && !warned) {
 			// like a gzread error upstream, a damaged file ends the input where the damage is -- but not silently
-			fprintf(stderr, "arcs: warning: %s: gzip stream ends early: %s\n", path.c_str(), (par ? par->error() : inf->error()).c_str());
+			fprintf(stderr, "arcs: warning: %s: gzip stream ends early: %s\n", path.c_str(),
+			    (bgzf ? bgzf->error() : par ? par->error() : inf->error()).c_str());
 			warned = true;
 		}
 		return got;

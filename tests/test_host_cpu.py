@@ -467,6 +467,117 @@ def test_par_inflate_members_garbage_truncation_corruption(tmp_path):
         assert err is not None or out == a
 
 
+# ---- bgzf_inflate.h (bgzip's many small members, dealt out to threads) ---------------------------------------
+def _bgzf_member(chunk, level=6, extra_subfields=b""):
+    import struct
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    d = c.compress(chunk) + c.flush()
+    xlen = 6 + len(extra_subfields)
+    bsize = 12 + xlen + len(d) + 8
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", xlen) + extra_subfields + b"BC\x02\0" + struct.pack("<H", bsize - 1) + d +
+            struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+
+
+def _bgzf(data, block=65280, level=6, eof=True, **kw):
+    out = [_bgzf_member(data[i:i + block], level, **kw) for i in range(0, len(data), block)]
+    if eof:
+        out.append(_bgzf_member(b""))
+    return b"".join(out)
+
+
+def _bgzf_inflate(path, threads=4, wave=1 << 16, chunk=1 << 20):
+    p = subprocess.run([INFLATE, "bgzf%d" % threads, str(path), str(chunk)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True,
+                       env=dict(os.environ, PAR_CHUNK=str(wave)))
+    lines = p.stderr.decode().splitlines()
+    err = [ln for ln in lines if ln.startswith("ERROR")]
+    members = [int(ln.split()[1]) for ln in lines if ln.startswith("PARALLEL_MEMBERS")]
+    is_bgzf = [int(ln.split()[1]) for ln in lines if ln.startswith("IS_BGZF")]
+    return p.stdout, (err[0] if err else None), (members[0] if members else 0), bool(is_bgzf and is_bgzf[0])
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_bgzf_inflate_fastq(threads, tmp_path):
+    _build_inflate()
+    data = _big_fastq(20000, 50 + threads)
+    path = tmp_path / "r.fq.gz"
+    blob = _bgzf(data, level=threads)
+    assert gzip.decompress(blob) == data  # the writer above makes valid gzip
+    path.write_bytes(blob)
+    out, err, members, is_bgzf = _bgzf_inflate(path, threads, wave=1 << 18)
+    assert is_bgzf and err is None and out == data
+    assert members == (len(data) + 65279) // 65280 + 1
+    out, err, _, _ = _bgzf_inflate(path, threads, wave=1 << 16, chunk=4099)
+    assert err is None and out == data
+
+
+@pytest.mark.parametrize("name", sorted(_payloads()))
+def test_bgzf_inflate_any_payload(name, tmp_path):
+    _build_inflate()
+    data = _payloads()[name]
+    for i, (block, level, eof) in enumerate([(65280, 6, True), (65000, 0, True), (1000, 1, False), (7, 9, True)]):
+        if block < 100:
+            data = data[:5000]
+        path = tmp_path / ("v%d.gz" % i)
+        path.write_bytes(_bgzf(data, block, level, eof))
+        out, err, _, _ = _bgzf_inflate(path, 4)
+        assert err is None, (name, block, level, err)
+        assert out == data, (name, block, level)
+    # other extra sub-fields in front of BC are skipped
+    (tmp_path / "x.gz").write_bytes(_bgzf(data, 3000, extra_subfields=b"XY\x03\0abc"))
+    out, err, members, is_bgzf = _bgzf_inflate(tmp_path / "x.gz", 4)
+    assert is_bgzf and err is None and out == data and members > 0
+
+
+def test_bgzf_inflate_mixed_members_garbage_truncation_corruption(tmp_path):
+    _build_inflate()
+    a, b, c = _big_fastq(6000, 11), _big_fastq(2000, 12), _big_fastq(1000, 13)
+    # concatenated bgzf files (an empty end-of-file member in the middle), then a plain gzip member, then bgzf again
+    # (sequential by then), then padding
+    (tmp_path / "m.gz").write_bytes(_bgzf(a) + _bgzf(b, 20000) + _gz(c, 6) + _bgzf(a[:100000]) + b"\0" * 13)
+    out, err, members, is_bgzf = _bgzf_inflate(tmp_path / "m.gz", 4)
+    assert is_bgzf and err is None and out == a + b + c + a[:100000]
+    assert members == (len(a) + 65279) // 65280 + 1 + (len(b) + 19999) // 20000 + 1
+    # a plain gzip file is not bgzf; the decoder still reads it (all of it through the sequential decoder)
+    (tmp_path / "p.gz").write_bytes(_gz(b, 6))
+    out, err, members, is_bgzf = _bgzf_inflate(tmp_path / "p.gz", 4)
+    assert not is_bgzf and err is None and out == b and members == 0
+    blob = _bgzf(a)
+    for cut in (len(blob) - 1, len(blob) - 29, len(blob) // 2, len(blob) // 3, 40, 17):
+        (tmp_path / "t.gz").write_bytes(blob[:cut])
+        out, err, _, _ = _bgzf_inflate(tmp_path / "t.gz", 4)
+        assert a.startswith(out), cut
+        assert err is not None, cut
+    (tmp_path / "t.gz").write_bytes(blob[:-28])  # without the end-of-file member: still every byte
+    out, err, _, _ = _bgzf_inflate(tmp_path / "t.gz", 4)
+    assert err is None and out == a
+    rng = np.random.default_rng(4)
+    for t in range(40):
+        d = bytearray(blob)
+        d[int(rng.integers(0, len(d)))] ^= 1 << int(rng.integers(0, 8))
+        (tmp_path / "c.gz").write_bytes(bytes(d))
+        out, err, _, _ = _bgzf_inflate(tmp_path / "c.gz", 4)
+        assert err is not None or out == a, t
+        if err is not None:
+            # what was delivered in front of the damage is right, except where the damage went to the sequential
+            # decoder in the middle of a member (a broken header): then a prefix plus that decoder's bytes
+            assert a.startswith(out[:(len(out) // 65280) * 65280]), t
+
+
+def test_ingest_through_the_bgzf_decoder(tmp_path):
+    _build_ingest()
+    rng = np.random.default_rng(32)
+    data = _strict_fastq(rng, 12000, barcodes=40, tweak=_tweak_pairing)
+    path = tmp_path / "reads.fq.gz"
+    path.write_bytes(_bgzf(data))
+    ref = subprocess.run([INGEST, "seq", str(path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True,
+                         env=dict(os.environ, ARKS_ZLIB="1")).stdout
+    for threads in ("1", "4"):
+        got = subprocess.run([INGEST, "par", str(path), "4", str(1 << 18)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True,
+                             env=dict(os.environ, ARKS_GZ_THREADS=threads)).stdout
+        assert got == ref, threads
+
+
 def test_ingest_through_the_parallel_gzip_decoder(tmp_path):
     """the whole read ingest (block-parallel parser) behind the multi-threaded gzip decoder gives the pairs,
     counters and multiplicities of the sequential reader behind zlib"""
