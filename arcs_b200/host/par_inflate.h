@@ -414,8 +414,8 @@ class ParInflate
 	}
 	ParInflate(const ParInflate&) = delete;
 	ParInflate& operator=(const ParInflate&) = delete;
-	bool ok() const { return m_err.empty() && (!m_seq || m_seq->ok()); }
-	std::string error() const { return !m_err.empty() ? m_err : (m_seq ? m_seq->error() : std::string()); }
+	bool ok() const { return m_read_err.empty() && (!m_read_seq || m_read_seq->ok()); }
+	std::string error() const { return !m_read_err.empty() ? m_read_err : (m_read_seq ? m_read_seq->error() : std::string()); }
 	size_t parallel_chunks() const { return m_par_chunks; }
 
 	long read(char* dst, size_t n)
@@ -454,10 +454,15 @@ class ParInflate
 				}
 			}
 			// the producer has stopped: error, end of the member, or the sequential decoder takes over
-			if (!m_err.empty())
+			if (!m_taken_over) { // (its verdict crosses to the reading thread here, after m_producer_done was seen under the lock)
+				m_read_err = std::move(m_err);
+				m_read_seq = std::move(m_seq);
+				m_taken_over = true;
+			}
+			if (!m_read_err.empty())
 				break;
-			if (m_seq) {
-				const long r = m_seq->read(dst + got, n - got);
+			if (m_read_seq) {
+				const long r = m_read_seq->read(dst + got, n - got);
 				if (r <= 0)
 					break;
 				got += (size_t)r;
@@ -735,8 +740,11 @@ class ParInflate
 	std::mutex m_mu;
 	std::condition_variable m_cv;
 	bool m_quit = false, m_producer_done = false;
-	std::unique_ptr<FastInflate> m_seq;
+	std::unique_ptr<FastInflate> m_seq; // (the producer's; read() and ok() see m_read_seq / m_read_err)
 	std::string m_err;
+	std::unique_ptr<FastInflate> m_read_seq;
+	std::string m_read_err;
+	bool m_taken_over = false;
 };
 
 } // namespace arks_host
