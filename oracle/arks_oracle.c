@@ -48,6 +48,8 @@ arks_oracle_key(const char* win, int k, uint8_t* key)
 	int nb = (k + 3) / 4;
 	int code[4 * ARKS_ORACLE_MAX_KEY_BYTES];
 	int i;
+	if (k <= 0 || k > 4 * ARKS_ORACLE_MAX_KEY_BYTES)
+		return 0;
 	for (i = 0; i < k; ++i) {
 		code[i] = base_code(win[i]);
 		if (code[i] < 0)
