@@ -22,6 +22,7 @@
 //    the IndexMap rows to the same GPU pair-link kernel.
 #include "../../include/arks_b200.h"
 #include "ingest.h"
+#include "long_cut.h"
 #include "seq_reader.h"
 
 #include <algorithm>
@@ -70,6 +71,7 @@ struct Params
 	bool arks = false, dist_est = false, output_pair = false, dist_upper = false;
 	int gpus = 1;
 	bool two_pass = false;
+	size_t cut = 0, cut_min = 2000; // --cut / --cut_min: the inputs are long reads, cut on the fly (long_cut.h)
 };
 Params params;
 
@@ -97,6 +99,9 @@ const char USAGE[] =
     "   -P, --pair            output scaffolds pairing TSV\n"
     "   -v, --run_verbose     verbose logging\n"
     "       --gpus=N          number of GPUs to shard read pairs over [1]\n"
+    "       --cut=L           the read files hold long reads: cut them into pseudo-linked read pairs of\n"
+    "                         L bases while reading (what `long-to-linked-pe -l L` would pipe in)\n"
+    "       --cut_min=M       with --cut: minimum length of a long read [2000]\n"
     "       --arks            k-mer method (required)\n";
 
 enum
@@ -114,7 +119,9 @@ enum
 	OPT_DIST_UPPER,
 	OPT_ARKS_METHOD,
 	OPT_GPUS,
-	OPT_TWO_PASS
+	OPT_TWO_PASS,
+	OPT_CUT,
+	OPT_CUT_MIN
 };
 
 const char shortopts[] = "f:a:B:s:c:Dl:z:b:g:m:d:e:r:vt:u:j:k:P";
@@ -152,7 +159,28 @@ const struct option longopts[] = { { "file", required_argument, NULL, 'f' },
 	                               { "pair", no_argument, NULL, 'P' },
 	                               { "gpus", required_argument, NULL, OPT_GPUS },
 	                               { "two-pass", no_argument, NULL, OPT_TWO_PASS },
+	                               { "cut", required_argument, NULL, OPT_CUT },
+	                               { "cut_min", required_argument, NULL, OPT_CUT_MIN },
 	                               { NULL, 0, NULL, 0 } };
+
+// A read file as a byte stream: the file itself, or -- with --cut -- the pseudo-linked reads cut from the
+// long reads in it.  Exits like the reference when the file cannot be opened (Arcs.cpp:1166-1170).
+std::unique_ptr<arks_host::ByteSource> open_reads(const std::string& f)
+{
+	std::unique_ptr<arks_host::ByteSource> src;
+	if (params.cut) {
+		std::unique_ptr<arks_host::LongCutSource> cut(new arks_host::LongCutSource(f, params.cut, params.cut_min));
+		if (cut->ok())
+			src = std::move(cut);
+	} else {
+		src = arks_host::open_source(f);
+	}
+	if (!src) {
+		std::cerr << "File " << f << " cannot be opened." << std::endl;
+		exit(1);
+	}
+	return src;
+}
 
 [[noreturn]] void die(const std::string& msg)
 {
@@ -211,6 +239,8 @@ bool check_same_format(const std::vector<std::string>& files, bool& all_alignmen
 		if (f.find(".sam") != std::string::npos || f.find(".bam") != std::string::npos)
 			cur = 1;
 		if (f.find(".fastq") != std::string::npos || f.find(".fq") != std::string::npos)
+			cur = 2;
+		if (params.cut && !cur && f.find(".fa") != std::string::npos) // long reads to cut (--cut) also come as FASTA
 			cur = 2;
 		if (!cur) {
 			std::cout << "Unknown type file is observed!" << std::endl;
@@ -939,6 +969,14 @@ int main(int argc, char** argv)
 		case OPT_BX: break;
 		case OPT_GPUS: arg >> params.gpus; break;
 		case OPT_TWO_PASS: params.two_pass = true; break;
+		case OPT_CUT:
+			arg >> params.cut;
+			arksOnly = true;
+			break;
+		case OPT_CUT_MIN:
+			arg >> params.cut_min;
+			arksOnly = true;
+			break;
 		case 'm': {
 			std::string a, b;
 			std::getline(arg, a, '-');
@@ -1107,11 +1145,7 @@ int main(int argc, char** argv)
 		// readBarcodes (Arcs.cpp:481-547)
 		std::string scratch;
 		for (const auto& f : filenames) {
-			SeqReader rd(f);
-			if (!rd.ok()) {
-				std::cerr << "File " << f << " cannot be opened." << std::endl;
-				exit(1);
-			}
+			SeqReader rd(open_reads(f), std::string());
 			SeqRecord r;
 			while (rd.read(r) > 0) {
 				r.truncate_at_nul();
@@ -1276,20 +1310,15 @@ int main(int argc, char** argv)
 				}
 				std::cerr << "File " << f << " opened." << std::endl;
 				size_t nb = 0;
-				if (!arks_host::ingest_parallel_blocks(f, bc, cfg, counting, ictr, sink, popt, &nb)) {
+				if (!arks_host::ingest_parallel_blocks(f, bc, cfg, counting, ictr, sink, popt, &nb, params.cut ? open_reads(f) : nullptr)) {
 					std::cerr << "File " << f << " cannot be opened." << std::endl;
 					exit(1);
 				}
 				fast_blocks += nb;
 				continue;
 			}
-			SeqReader rd(f);
-			if (!rd.ok()) {
-				std::cerr << "File " << f << " cannot be opened." << std::endl;
-				exit(1);
-			} else {
-				std::cerr << "File " << f << " opened." << std::endl;
-			}
+			SeqReader rd(open_reads(f), std::string());
+			std::cerr << "File " << f << " opened." << std::endl;
 			arks_host::ingest_sequential(rd, bc, cfg, counting, ictr, sink);
 		}
 		for (auto& g : gpus)

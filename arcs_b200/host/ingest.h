@@ -441,11 +441,17 @@ class ParallelIngest
 
 	// `frozen` (only with cfg.mult_known): the barcode table, which must not change until finish() returns.
 	// Returns false if the file cannot be opened.
-	bool start(const std::string& path, const IngestConfig& cfg, const ParallelIngestOptions& opt, const Barcodes* frozen)
+	// `src`: an already opened stream to read instead of `path` (e.g. long reads cut on the fly, long_cut.h).
+	bool start(const std::string& path, const IngestConfig& cfg, const ParallelIngestOptions& opt, const Barcodes* frozen,
+	    std::unique_ptr<ByteSource> src = nullptr)
 	{
 		m_cfg = cfg;
 		m_opt = opt;
 		m_frozen = frozen;
+		if (src) {
+			m_src = std::move(src);
+			return launch();
+		}
 		// plain regular files are memory-mapped (blocks are cut in place, nothing is copied); gzip files (fast
 		// decoder) and pipes (zlib, transparent for plain data) are read into block buffers
 		m_fd = ::open(path.c_str(), O_RDONLY);
@@ -470,6 +476,12 @@ class ParallelIngest
 			if (!m_src)
 				return false;
 		}
+		return launch();
+	}
+
+  private:
+	bool launch()
+	{
 		m_bufs.resize(m_opt.slots.size());
 		for (size_t i = 0; i < m_opt.slots.size(); ++i)
 			m_free_slots.push_back((int)i);
@@ -479,6 +491,8 @@ class ParallelIngest
 			m_workers.emplace_back([this] { worker_loop(); });
 		return true;
 	}
+
+  public:
 
 	void finish(Barcodes& bc, bool& counting, IngestCounters& ctr, PairSink& sink, size_t* n_fast_blocks = nullptr)
 	{
@@ -721,10 +735,10 @@ class ParallelIngest
 };
 
 inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const IngestConfig& cfg, bool& counting, IngestCounters& ctr,
-    PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr)
+    PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr, std::unique_ptr<ByteSource> src = nullptr)
 {
 	ParallelIngest pi;
-	if (!pi.start(path, cfg, opt, cfg.mult_known ? &bc : nullptr))
+	if (!pi.start(path, cfg, opt, cfg.mult_known ? &bc : nullptr, std::move(src)))
 		return false;
 	pi.finish(bc, counting, ctr, sink, n_fast_blocks);
 	return true;

@@ -5,6 +5,7 @@
 // Output: one "P <barcode> <mate1> <mate2>" line per accepted pair (input order), the counters, the
 // number of blocks that went through the parallel path, and the barcode table sorted by name.
 #include "ingest.h"
+#include "long_cut.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +59,18 @@ int main(int argc, char** argv)
 	};
 	bool counting = !cfg.mult_known;
 	size_t fast = 0;
+	// ARKS_CUT=L,M: `path` holds long reads, cut on the fly like `arcs --arks --cut L --cut_min M`
+	size_t cut_l = 0, cut_m = 2000;
+	if (const char* e = getenv("ARKS_CUT"))
+		sscanf(e, "%zu,%zu", &cut_l, &cut_m);
+	auto cut_source = [&]() -> std::unique_ptr<arks_host::ByteSource> {
+		if (!cut_l)
+			return nullptr;
+		std::unique_ptr<arks_host::LongCutSource> src(new arks_host::LongCutSource(path, cut_l, cut_m));
+		if (!src->ok())
+			exit(3);
+		return src;
+	};
 	if (par) {
 		ParallelIngestOptions opt;
 		opt.workers = argc > 3 ? atoi(argv[3]) : 4;
@@ -76,8 +89,11 @@ int main(int argc, char** argv)
 			pb.cap_pairs = cap_pairs;
 			opt.slots.push_back(pb);
 		}
-		if (!ingest_parallel_blocks(path, bc, cfg, counting, ctr, sink, opt, &fast))
+		if (!ingest_parallel_blocks(path, bc, cfg, counting, ctr, sink, opt, &fast, cut_source()))
 			return 3;
+	} else if (cut_l) {
+		SeqReader rd(cut_source(), std::string());
+		ingest_sequential(rd, bc, cfg, counting, ctr, sink);
 	} else {
 		SeqReader rd(path);
 		if (!rd.ok())

@@ -14,6 +14,7 @@
 //
 // Option handling follows the reference's getopt table including its quirks: `-t` has no `break`
 // (:118-120), so its argument also becomes the -f file name; `-v` and `-o` are rejected.
+#include "long_cut.h"
 #include "seq_reader.h"
 
 #include <algorithm>
@@ -63,24 +64,6 @@ void print_usage()
 	          << std::endl;
 }
 
-// complement table: nucleotides and IUPAC ambiguity codes, case preserved, everything else unchanged
-struct Complement
-{
-	unsigned char t[256];
-	Complement()
-	{
-		for (int i = 0; i < 256; ++i)
-			t[i] = (unsigned char)i;
-		const char* from = "ACGTURYSWKMBDHVN";
-		const char* to = "TGCAAYRSWMKVHDBN";
-		for (int i = 0; from[i]; ++i) {
-			t[(unsigned char)from[i]] = (unsigned char)to[i];
-			t[(unsigned char)(from[i] | 0x20)] = (unsigned char)(to[i] | 0x20);
-		}
-	}
-};
-const Complement kComp;
-
 // stdout through one large buffer (the reference flushes per record; the bytes are the same)
 struct Out
 {
@@ -104,18 +87,6 @@ struct Out
 		fflush(stdout);
 	}
 };
-
-void append_revcomp(std::string& out, const std::string& s, size_t pos, size_t n)
-{
-	for (size_t i = 0; i < n; ++i)
-		out.push_back((char)kComp.t[(unsigned char)s[pos + n - 1 - i]]);
-}
-
-void append_reversed(std::string& out, const std::string& s, size_t pos, size_t n)
-{
-	for (size_t i = 0; i < n; ++i)
-		out.push_back(s[pos + n - 1 - i]);
-}
 
 } // namespace
 
@@ -210,13 +181,15 @@ int main(int argc, char* argv[])
 		          << std::flush;
 	}
 
-	const char header_symbol = with_fasta ? '>' : '@';
 	std::ofstream bx_multiplicity_ofs;
 	if (with_bx_multiplicity_only || with_bx_multiplicity)
 		bx_multiplicity_ofs = std::ofstream(bxMultiplicityFile, std::ofstream::out);
 
 	Out out;
-	std::string header;
+	arks_host::LongCutter cutter;
+	cutter.l = l;
+	cutter.m = m;
+	cutter.fasta = with_fasta != 0;
 	for (auto& infile : infiles) {
 		arks_host::SeqReader reader(infile, 1u << 22);
 		if (!reader.ok()) {
@@ -239,8 +212,6 @@ int main(int argc, char* argv[])
 			}
 			if (with_bx_multiplicity_only)
 				continue;
-			const std::string& qual = record.qual;
-			const size_t qual_size = qual.size();
 			if (auto_dist && seq_size > dist_lower_bound)
 				read_lengths.push_back(seq_size);
 			if (auto_span)
@@ -248,51 +219,7 @@ int main(int argc, char* argv[])
 			if (step > seq_size || m > seq_size)
 				continue;
 
-			const std::string bx = " BX:Z:" + std::to_string(num + 1) + "\n";
-			std::string& o = out.buf;
-			auto emit_header = [&](int read_num) {
-				o.push_back(header_symbol);
-				o += record.name;
-				o += "_f";
-				o += std::to_string(read_num);
-				o += bx;
-			};
-			// one pseudo pair: forward piece [fpos, fpos + n), reverse-complemented piece [rpos, rpos + n)
-			auto emit_pair = [&](int read_num, size_t fpos, size_t rpos, size_t n) {
-				emit_header(read_num);
-				o.append(seq, fpos, n);
-				o.push_back('\n');
-				if (!with_fasta) {
-					o += "+\n";
-					if (qual_size == 0)
-						o.append(n, '#');
-					else
-						o.append(qual, fpos, std::min(n, qual_size > fpos ? qual_size - fpos : 0));
-					o.push_back('\n');
-				}
-				emit_header(read_num);
-				append_revcomp(o, seq, rpos, n);
-				o.push_back('\n');
-				if (!with_fasta) {
-					o += "+\n";
-					if (qual_size == 0)
-						o.append(n, '#');
-					else
-						append_reversed(o, qual, rpos, n);
-					o.push_back('\n');
-				}
-			};
-			int read_num = 1;
-			for (size_t i = 0; i <= seq_size - step; i += step) {
-				emit_pair(read_num, i, i + l, l);
-				++read_num;
-			}
-			const size_t remainder = seq_size % step;
-			if (remainder != 0) {
-				const size_t curr_i = seq_size - remainder;
-				const size_t n = std::min(l, remainder); // seq.substr(curr_i, l).size()
-				emit_pair(read_num, curr_i, seq_size - n, n);
-			}
+			cutter.append_pairs(out.buf, record, num);
 			out.maybe_flush();
 		}
 	}

@@ -103,3 +103,32 @@ def test_usage_errors(tmp_path):
     assert p.returncode != 0 and b"missing option -- 'l'" in p.stderr
     p = subprocess.run([TOOL, "-l", "250"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode != 0 and b"missing file operand" in p.stderr
+
+
+# ---- `arcs --arks --cut L`: the same bytes without the tool and the pipe (arcs_b200/host/long_cut.h) ---------
+INGEST = os.path.join(ROOT, "arcs_b200", "bin", "ingest_dump")
+
+
+@pytest.mark.parametrize("reads,l,m", [
+    (os.path.join(ROOT, "tests", "golden", "cli_cases", "cut_k20", "long_reads.fa.gz"), 250, 2000),
+    (os.path.join(ROOT, "tests", "golden", "cli_cases", "cut_k20", "long_reads.fa.gz"), 100, 0),
+    (os.path.join(GOLD, "test_reads.head60.fa.gz"), 250, 2000),
+    (os.path.join(GOLD, "test_reads.head60.fa.gz"), 1500, 500),
+])
+def test_cutting_inside_the_ingest_equals_the_pipe(reads, l, m, tmp_path):
+    """what the read ingest of the CLI sees with --cut (pairs, barcodes, counters, multiplicities) is what it
+    sees when the tool's output is fed to it, for the sequential reader and the block-parallel one"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "arcs_b200", "host"), "../bin/ingest_dump", "../bin/long-to-linked-pe"])
+    cut = tmp_path / "cut.fq"
+    with open(cut, "wb") as o:
+        subprocess.check_call([TOOL, "-l", str(l), "-m", str(m), reads], stdout=o, stderr=subprocess.DEVNULL)
+    want = subprocess.run([INGEST, "seq", str(cut)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    assert want.count(b"\n") > 50
+    env = dict(os.environ, ARKS_CUT="%d,%d" % (l, m))
+    got = subprocess.run([INGEST, "seq", reads], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True, env=env).stdout
+    assert got == want
+    for workers, block in ((1, 1 << 16), (4, 1 << 15), (3, 1 << 20)):
+        p = subprocess.run([INGEST, "par", reads, str(workers), str(block)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True, env=env)
+        assert p.stdout == want, (workers, block)
+        if block < (1 << 20):  # the cut reads are strict four-line FASTQ: the block parser takes them
+            assert int(p.stderr.decode().split("FAST_BLOCKS")[1].split()[0]) > 0

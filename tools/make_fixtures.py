@@ -226,6 +226,66 @@ def make_sam_case():
         json.dump({"args": args, "multfile": None, "mode": "arcs", "with_f": with_f}, open(base + "_args.json", "w"))
 
 
+def make_cut_case():
+    """arks-long without the pipe: long reads in, `arcs --arks --cut 250` must give what the
+    reference's code gives on the output of long-to-linked-pe (our drop-in of that tool is pinned byte for byte
+    on the reference's own golden, tests/test_long_to_linked_pe.py)."""
+    import tempfile
+    ltlpe = os.path.join(ROOT, "arcs_b200", "bin", "long-to-linked-pe")
+    rng = np.random.default_rng(21)
+    k = 20
+    genome, contigs = synth.make_draft(rng, 120000, 10000, k, n_runs=6, palindromes=3, iupac=3)
+    d = os.path.join(OUT, "cut_k20")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "draft.fa"), "w") as f:
+        for cname, s, e in contigs:
+            f.write(">%s\n%s\n" % (cname, wrap(genome[s:e].tobytes().decode(), 100)))
+    comp = bytes.maketrans(b"ACGTacgtNn", b"TGCAtgcaNn")
+    with gzip.open(os.path.join(d, "long_reads.fa.gz"), "wt") as f:
+        for i in range(130):
+            L = int(np.clip(rng.lognormal(np.log(6000), 0.7), 400, 30000))  # some are shorter than --cut_min
+            a = int(rng.integers(0, len(genome) - L))
+            r = genome[a:a + L].copy()
+            sub = rng.random(L) < 0.03  # long-read error rate (substitutions only: the cut positions stay put)
+            r[sub] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(sub.sum()))]
+            if i % 9 == 0:  # N-rich stretch: some pseudo reads exceed the 2 % N limit
+                p = int(rng.integers(0, L - 300))
+                r[p:p + 300][rng.random(300) < 0.1] = ord("N")
+            if i % 11 == 3:
+                r[int(rng.integers(0, L))] = ord("R")  # IUPAC: that pseudo pair is invalid
+            seq = r.tobytes()
+            if i % 2:
+                seq = seq.translate(comp)[::-1]
+            seq = seq.decode()
+            if i % 5 == 4:  # a FASTQ record among the FASTA ones
+                f.write("@lr%d extra words\n%s\n+\n%s\n" % (i, seq, "".join(chr(33 + (j * 7 + i) % 40) for j in range(L))))
+            else:
+                f.write(">lr%d len=%d\n%s\n" % (i, L, wrap(seq, 80)))
+    reads = os.path.join(d, "long_reads.fa.gz")
+    with tempfile.TemporaryDirectory() as t:
+        cut = os.path.join(t, "cut.fq")
+        with open(cut, "wb") as o:
+            subprocess.check_call([ltlpe, "-l", "250", "-m", "2000", reads], stdout=o, stderr=subprocess.DEVNULL)
+        mult = os.path.join(d, "mult.tsv")
+        subprocess.check_call([ltlpe, "-l", "250", "-m", "2000", "--bx-only", "-b", mult, reads], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        # drop a few barcodes from the multiplicity file: their pairs are rejected as invalid barcodes
+        lines = open(mult).read().splitlines()
+        open(mult, "w").write("\n".join(ln for i, ln in enumerate(lines) if i % 13 != 5) + "\n")
+        for tag, args, mf in (("a", ["-k", "20", "-j", "0.05", "-c", "2", "-m", "4-10000", "-e", "30000", "-z", "500", "-r", "0.05", "-t", "1"], None),
+                              ("u", ["-k", "20", "-j", "0.05", "-c", "3", "-m", "8-10000", "-e", "3000", "-z", "500", "-r", "0.05", "-t", "1"], mult)):
+            base = os.path.join(d, "expected_" + tag)
+            cmd = [REF, "-f", os.path.join(d, "draft.fa"), "-b", base, "--tsv", base + "_main.tsv", "--barcode-counts", base + "_bc.tsv",
+                   "--dump-pmap", base + "_pmap.txt"] + args + (["-u", mf] if mf else []) + [cut]
+            subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            for junk in (base + ".dist.gv",):
+                if os.path.exists(junk):
+                    os.remove(junk)
+            json.dump({"args": args, "multfile": "mult.tsv" if mf else None, "cut": [250, 2000], "reads": "long_reads.fa.gz"},
+                      open(base + "_args.json", "w"))
+    return d
+
+
 def main():
     if not os.path.exists(REF):
         raise SystemExit("oracle/_ref/arcs_ref is missing: run oracle/build_ref.sh where /root/reference exists")
@@ -233,6 +293,8 @@ def main():
         return add_dist_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "sam":
         return make_sam_case()
+    if len(sys.argv) > 1 and sys.argv[1] == "cut":
+        return make_cut_case()
     if len(sys.argv) > 1 and sys.argv[1] == "shuffled":
         return add_shuffled_case()
     # case A: k=30 defaults-ish, adversarial FASTQ, contig names whose string order differs from numeric order
