@@ -397,7 +397,7 @@ class ParInflate
 	  , m_threads(std::max(1, threads))
 	  , m_chunk(std::max<size_t>(chunk_bytes, 1u << 16))
 	{
-		if (!parse_header())
+		if (!parse_header(0))
 			start_sequential_from_scratch();
 		else
 			m_producer = std::thread([this] { producer_loop(); });
@@ -474,13 +474,14 @@ class ParInflate
 	}
 
   private:
-	bool parse_header()
+	// the member header at byte `off`: on success the member's first block starts at m_pos
+	bool parse_header(size_t off)
 	{
-		// exactly one member without surprises: magic, deflate, no reserved flags; optional fields skipped
-		if (m_n < 18 + 8 || m_in[0] != 0x1f || m_in[1] != 0x8b || m_in[2] != 8 || (m_in[3] & 0xe0))
+		// a member without surprises: magic, deflate, no reserved flags; optional fields skipped
+		if (off + 18 + 8 > m_n || m_in[off] != 0x1f || m_in[off + 1] != 0x8b || m_in[off + 2] != 8 || (m_in[off + 3] & 0xe0))
 			return false;
-		const int flg = m_in[3];
-		size_t p = 10;
+		const int flg = m_in[off + 3];
+		size_t p = off + 10;
 		if (flg & 4) {
 			if (p + 2 > m_n)
 				return false;
@@ -498,12 +499,17 @@ class ParInflate
 			return false;
 		m_pos = (uint64_t)p * 8;
 		m_known_start = true;
+		m_member_off = off;
 		return true;
 	}
 
+	// the sequential decoder takes the member that starts at m_member_off, nothing of which has been delivered
 	void start_sequential_from_scratch()
 	{
-		m_seq.reset(new FastInflate(m_in, m_n));
+		if (m_member_off)
+			m_seq.reset(new FastInflate(m_in + m_member_off, m_n - m_member_off, FastInflate::AfterMember()));
+		else
+			m_seq.reset(new FastInflate(m_in, m_n));
 	}
 	// hands the rest of the stream to the sequential decoder at the block boundary m_pos
 	void start_sequential_here()
@@ -717,9 +723,16 @@ class ParInflate
 		else if (isize != (uint32_t)m_out_total)
 			m_err = "incorrect length check";
 		else if (t + 8 < m_n) {
-			// more members (or trailing bytes) follow: the sequential decoder takes them
-			m_seq.reset(new FastInflate(m_in + t + 8, m_n - t - 8, FastInflate::AfterMember()));
+			// more follows.  Another member of some size (files made with `cat a.gz b.gz`) is decoded like the first
+			// one; short members, padding and anything else are the sequential decoder's business
 			m_done = false;
+			if (m_n - (t + 8) >= (m_chunk << 2) && parse_header(t + 8)) {
+				m_crc = 0;
+				m_out_total = 0;
+				std::fill(m_window.begin(), m_window.end(), 0);
+				return;
+			}
+			m_seq.reset(new FastInflate(m_in + t + 8, m_n - t - 8, FastInflate::AfterMember()));
 		}
 	}
 
@@ -728,6 +741,7 @@ class ParInflate
 	int m_threads;
 	size_t m_chunk;
 	uint64_t m_pos = 0; // bit position of the next block (always a validated block boundary)
+	size_t m_member_off = 0; // byte offset of the member being decoded
 	bool m_known_start = false, m_done = false;
 	std::vector<uint8_t> m_window = std::vector<uint8_t>(32768, 0);
 	uint32_t m_crc = 0;

@@ -578,6 +578,31 @@ def test_ingest_through_the_bgzf_decoder(tmp_path):
         assert got == ref, threads
 
 
+def test_par_inflate_several_large_members(tmp_path):
+    """`cat a.fq.gz b.fq.gz c.fq.gz`: every member of some size is decoded by all threads, not only the first"""
+    _build_inflate()
+    parts = [_big_fastq(9000, 21), _big_fastq(7000, 22), _big_fastq(300, 23), _big_fastq(8000, 24)]
+    blobs = [_gz(parts[0], 6), _gz(parts[1], 1), _gz(parts[2], 9), _gz(parts[3], 4)]
+    (tmp_path / "m.gz").write_bytes(b"".join(blobs))
+    only_first = None
+    for threads in (2, 4):
+        out, err, nchunks = _par_inflate(tmp_path / "m.gz", threads, par_chunk=1 << 16)
+        assert err is None and out == b"".join(parts)
+        (tmp_path / "first.gz").write_bytes(blobs[0])
+        only_first = _par_inflate(tmp_path / "first.gz", threads, par_chunk=1 << 16)[2]
+        assert nchunks > 2 * only_first  # the later members went through the parallel decoder too
+    # damage in a later member: everything in front of it is still delivered, and the error is reported
+    bad = bytearray(b"".join(blobs))
+    bad[len(blobs[0]) + len(blobs[1]) // 2] ^= 0x10
+    (tmp_path / "bad.gz").write_bytes(bytes(bad))
+    out, err, _ = _par_inflate(tmp_path / "bad.gz", 4, par_chunk=1 << 16)
+    assert err is not None and out.startswith(parts[0]) and (parts[0] + parts[1]).startswith(out[:len(parts[0]) + 1000])
+    # a second member that is cut off
+    (tmp_path / "cut.gz").write_bytes(blobs[0] + blobs[1][:len(blobs[1]) // 2])
+    out, err, _ = _par_inflate(tmp_path / "cut.gz", 4, par_chunk=1 << 16)
+    assert err is not None and out.startswith(parts[0]) and (parts[0] + parts[1]).startswith(out)
+
+
 def test_ingest_through_the_parallel_gzip_decoder(tmp_path):
     """the whole read ingest (block-parallel parser) behind the multi-threaded gzip decoder gives the pairs,
     counters and multiplicities of the sequential reader behind zlib"""
