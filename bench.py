@@ -361,7 +361,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(2, args.warmup - 1)):  # never fewer than three untimed passes (the counted one included)
         step_device()
     barrier()
     clocks = ClockSampler(local)
