@@ -188,7 +188,7 @@ class BgzfInflate
 		W.good_bytes = 0;
 		size_t out = 0;
 		bool bgzf = true;
-		while (m_pos < m_n && out < m_wave_bytes) {
+		while (m_pos < m_n && out < m_wave_bytes && W.members.size() < (1u << 16)) {
 			Member m;
 			if (!parse_member(m_in, m_n, m_pos, m)) {
 				bgzf = false;
