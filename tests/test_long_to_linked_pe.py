@@ -132,3 +132,19 @@ def test_cutting_inside_the_ingest_equals_the_pipe(reads, l, m, tmp_path):
         assert p.stdout == want, (workers, block)
         if block < (1 << 20):  # the cut reads are strict four-line FASTQ: the block parser takes them
             assert int(p.stderr.decode().split("FAST_BLOCKS")[1].split()[0]) > 0
+
+
+def test_cut_option_checks_of_the_cli(tmp_path):
+    """--cut is an --arks option like -k / -j / -t (Arcs.cpp:2087-2091), and only with it are FASTA names
+    accepted as read files (checkSameFormat, Arcs.cpp:336-361, knows .fq / .fastq only)"""
+    arcs = os.path.join(ROOT, "arcs_b200", "bin", "arcs")
+    d = os.path.join(ROOT, "tests", "golden", "cli_cases", "cut_k20")
+    run = lambda args: subprocess.run([arcs] + args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    p = run(["--cut", "250", "-f", os.path.join(d, "draft.fa"), os.path.join(d, "long_reads.fa.gz")])
+    assert p.returncode != 0 and "does not match with method" in p.stderr
+    p = run(["--arks", "-k", "20", "-f", os.path.join(d, "draft.fa"), "-b", "x", os.path.join(d, "long_reads.fa.gz")])
+    assert p.returncode != 0 and "Unknown type file" in p.stdout
+    p = run(["--arks", "--cut", "250", "-k", "20", "-f", os.path.join(d, "draft.fa"), "-b", "x", os.path.join(d, "long_reads.fa.gz")])
+    # past the option checks: either it runs (GPU present) or the GPU initialisation fails loudly
+    assert "Unknown type file" not in p.stdout and "does not match" not in p.stderr
+    assert p.returncode == 0 or "no CPU fallback" in p.stderr

@@ -55,11 +55,3 @@ def test_cut_long_reads_on_the_fly(argsfile, mode, tmp_path):
     assert read(tmp_path / "o_main.tsv") == read(exp + "_main.tsv")
     assert read(tmp_path / "o_pair.tsv") == read(exp + "_pmap.txt")
     assert read(tmp_path / "bc.tsv") == read(exp + "_bc.tsv")
-
-
-def test_cut_is_an_arks_option(tmp_path):
-    """like -k / -j / -t, --cut does not go with the alignment method (Arcs.cpp:2087-2091)"""
-    p = subprocess.run([ARCS, "--cut", "250", "-f", os.path.join(GOLD, "draft.fa"), os.path.join(GOLD, "long_reads.fa.gz")], cwd=tmp_path,
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
-    assert p.returncode != 0
-    assert "does not match with method" in p.stderr
