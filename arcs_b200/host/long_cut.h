@@ -42,6 +42,13 @@ struct LongCutter
 
 	bool accepts(size_t seq_size) const { return !(2 * l > seq_size || m > seq_size); }
 
+	// reads of the barcode in the output: what --bx / --bx-only write (:236-246)
+	size_t multiplicity(size_t seq_size) const
+	{
+		const size_t step = 2 * l;
+		return seq_size % step != 0 ? (seq_size / step + 1) * 2 : seq_size / l;
+	}
+
 	// appends the pseudo pairs of record number `num` (0-based) to `o`; the caller has checked accepts()
 	void append_pairs(std::string& o, const SeqRecord& record, size_t num) const
 	{

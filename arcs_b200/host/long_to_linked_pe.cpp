@@ -33,9 +33,9 @@ const std::string PROGNAME = "long-to-linked-pe";
 const std::string VERSION = "v1.0";
 const size_t MAX_THREADS = 6;
 
-void print_error_msg(const std::string& msg)
+void complain(const std::string& what)
 {
-	std::cerr << PROGNAME << ' ' << VERSION << ": " << msg << std::endl;
+	std::cerr << PROGNAME << ' ' << VERSION << ": " << what << std::endl;
 }
 
 void print_usage()
@@ -88,165 +88,185 @@ struct Out
 	}
 };
 
-} // namespace
-
-int main(int argc, char* argv[])
+// everything the command line says
+struct Options
 {
-	int c;
-	int optindex = 0;
-	static int help = 0, version = 0;
-	bool auto_span = false, auto_dist = false;
-	size_t l = 0, g = 0, t = 6, m = 2000;
-	bool g_set = false;
-	bool l_set = false;
-	double cov_to_span = 0.25;
-	double dist_read_perc = 50;
-	size_t dist_lower_bound = 1000;
-	std::vector<size_t> read_lengths;
-	size_t total_bases = 0;
-	static int with_fasta = 0, with_bx_multiplicity = 0, with_bx_multiplicity_only = 0;
-	std::string configFile("tigmint-long.params.tsv");
-	std::string bxMultiplicityFile("barcode_multiplicity.tsv");
-	bool failed = false;
-	static const struct option longopts[] = { { "bx", no_argument, &with_bx_multiplicity, 1 },
-		                                      { "bx-only", no_argument, &with_bx_multiplicity_only, 1 },
-		                                      { "fasta", no_argument, &with_fasta, 1 },
-		                                      { "help", no_argument, &help, 1 },
-		                                      { "version", no_argument, &version, 1 },
-		                                      { nullptr, 0, nullptr, 0 } };
-	while ((c = getopt_long(argc, argv, "l:g:o:c:p:sdf:t:b:m:", longopts, &optindex)) != -1) {
-		switch (c) {
-		case 0: break;
-		case 'l':
-			l_set = true;
-			l = std::stoul(optarg);
-			break;
-		case 'm': m = std::stoul(optarg); break;
-		case 'g':
-			g_set = true;
-			g = (size_t)std::stod(optarg);
-			break;
-		case 'p': dist_read_perc = std::stod(optarg); break;
-		case 'c': cov_to_span = std::stod(optarg); break;
-		case 't':
-			t = std::stoul(optarg);
-			/* falls through, as in the reference (:118-120) */
-			/* fall through */
-		case 'f': configFile = optarg; break;
-		case 'b': bxMultiplicityFile = optarg; break;
-		case 's': auto_span = true; break;
-		case 'd': auto_dist = true; break;
-		default: std::exit(EXIT_FAILURE);
+	size_t read_len = 0;      // -l
+	bool have_read_len = false;
+	size_t genome_size = 0;   // -g (integer or scientific notation)
+	bool have_genome_size = false;
+	size_t threads = 6;       // -t (accepted; this tool is not bound by the cutting)
+	size_t min_long = 2000;   // -m
+	double span_factor = 0.25; // -c
+	double dist_percentile = 50; // -p
+	bool want_span = false, want_dist = false; // -s, -d
+	std::string params_file = "tigmint-long.params.tsv"; // -f
+	std::string mult_file = "barcode_multiplicity.tsv";  // -b
+	int fasta = 0, bx = 0, bx_only = 0, help = 0, version = 0;
+	std::vector<std::string> inputs;
+};
+
+// getopt table of the reference (src/long-to-linked-pe.cpp:86-139); an option it does not handle ends the program
+Options parse_command_line(int argc, char* argv[])
+{
+	static Options o; // (getopt_long stores the flags through pointers)
+	const struct option table[] = { { "bx", no_argument, &o.bx, 1 },
+		                            { "bx-only", no_argument, &o.bx_only, 1 },
+		                            { "fasta", no_argument, &o.fasta, 1 },
+		                            { "help", no_argument, &o.help, 1 },
+		                            { "version", no_argument, &o.version, 1 },
+		                            { nullptr, 0, nullptr, 0 } };
+	int idx = 0;
+	for (int c; (c = getopt_long(argc, argv, "l:g:o:c:p:sdf:t:b:m:", table, &idx)) != -1;) {
+		if (c == 0)
+			continue;
+		if (c == 'l') {
+			o.read_len = std::stoul(optarg);
+			o.have_read_len = true;
+		} else if (c == 'g') {
+			o.genome_size = (size_t)std::stod(optarg);
+			o.have_genome_size = true;
+		} else if (c == 'm') {
+			o.min_long = std::stoul(optarg);
+		} else if (c == 'p') {
+			o.dist_percentile = std::stod(optarg);
+		} else if (c == 'c') {
+			o.span_factor = std::stod(optarg);
+		} else if (c == 't' || c == 'f') {
+			// the reference's `case 't'` has no break (:118-120): the thread count also becomes the -f file name
+			if (c == 't')
+				o.threads = std::stoul(optarg);
+			o.params_file = optarg;
+		} else if (c == 'b') {
+			o.mult_file = optarg;
+		} else if (c == 's') {
+			o.want_span = true;
+		} else if (c == 'd') {
+			o.want_dist = true;
+		} else {
+			std::exit(EXIT_FAILURE); // unknown options, and -o, which is in the option string without a case
 		}
 	}
+	o.inputs.assign(argv + optind, argv + argc);
+	return o;
+}
 
-	std::vector<std::string> infiles(&argv[optind], &argv[argc]);
+// the reference's checks, in its order and with its messages (:141-182)
+void validate_or_exit(int argc, Options& o)
+{
 	if (argc < 2) {
 		print_usage();
 		std::exit(EXIT_FAILURE);
 	}
-	if (help != 0) {
+	if (o.help) {
 		print_usage();
 		std::exit(EXIT_SUCCESS);
-	} else if (version != 0) {
+	}
+	if (o.version) {
 		std::cerr << PROGNAME << ' ' << VERSION << std::endl;
 		std::exit(EXIT_SUCCESS);
 	}
-	if (!l_set) {
-		print_error_msg("missing option -- 'l'");
-		failed = true;
-	} else if (l == 0) {
-		print_error_msg("option has incorrect value -- 'l'");
-		failed = true;
-	}
-	if (!g_set && auto_span) {
-		print_error_msg("missing option -- 'g'");
-		failed = true;
-	} else if (g == 0 && auto_span) {
-		print_error_msg("option has incorrect value -- 'g'");
-		failed = true;
-	}
-	if (infiles.empty()) {
-		print_error_msg("missing file operand");
-		failed = true;
-	}
-	if (failed) {
+	int problems = 0;
+	if (!o.have_read_len)
+		complain("missing option -- 'l'"), ++problems;
+	else if (o.read_len == 0)
+		complain("option has incorrect value -- 'l'"), ++problems;
+	if (o.want_span && !o.have_genome_size)
+		complain("missing option -- 'g'"), ++problems;
+	else if (o.want_span && o.genome_size == 0)
+		complain("option has incorrect value -- 'g'"), ++problems;
+	if (o.inputs.empty())
+		complain("missing file operand"), ++problems;
+	if (problems) {
 		std::cerr << "Try '" << PROGNAME << " --help' for more information.\n";
 		std::exit(EXIT_FAILURE);
 	}
-	if (t > MAX_THREADS) {
-		t = MAX_THREADS;
+	if (o.threads > MAX_THREADS) {
+		o.threads = MAX_THREADS;
 		std::cerr << (PROGNAME + ' ' + VERSION + ": Using more than " + std::to_string(MAX_THREADS) +
 		              " threads does not scale, reverting to " + std::to_string(MAX_THREADS) + ".\n")
 		          << std::flush;
 	}
+}
 
-	std::ofstream bx_multiplicity_ofs;
-	if (with_bx_multiplicity_only || with_bx_multiplicity)
-		bx_multiplicity_ofs = std::ofstream(bxMultiplicityFile, std::ofstream::out);
+// what -s / -d append to the tigmint-long parameter file (:294-322)
+struct LengthStats
+{
+	std::vector<size_t> lengths; // of the reads longer than 1000 bases (-d)
+	size_t bases = 0;            // of all reads (-s)
 
-	Out out;
+	void write(const Options& o) const
+	{
+		std::ofstream f(o.params_file, std::ofstream::app);
+		if (o.want_span)
+			f << "span\t" << (size_t)(bases / o.genome_size * o.span_factor) << "\n";
+		if (!o.want_dist)
+			return;
+		if (lengths.empty()) {
+			std::cerr << "long-to-linked-pe: unable to estimate dist parameter due to no valid "
+			             "lengths"
+			          << std::endl;
+			return;
+		}
+		std::vector<size_t> sorted(lengths);
+		std::sort(sorted.begin(), sorted.end());
+		// the percentile as the reference takes it: the mean of two neighbours when the rank is whole
+		const double rank = (o.dist_percentile / 100) * sorted.size();
+		const size_t at = (size_t)floor(rank);
+		const size_t estimate = floor(rank) == rank ? (sorted[at - 1] + sorted[at]) / 2 : sorted[at];
+		f << "read_p" << o.dist_percentile << "\t" << estimate << "\n";
+	}
+};
+
+} // namespace
+
+int main(int argc, char* argv[])
+{
+	Options opt = parse_command_line(argc, argv);
+	validate_or_exit(argc, opt);
+
+	const bool count_bx = opt.bx || opt.bx_only;
+	std::ofstream mult_out;
+	if (count_bx)
+		mult_out.open(opt.mult_file, std::ofstream::out);
+
 	arks_host::LongCutter cutter;
-	cutter.l = l;
-	cutter.m = m;
-	cutter.fasta = with_fasta != 0;
-	for (auto& infile : infiles) {
-		arks_host::SeqReader reader(infile, 1u << 22);
+	cutter.l = opt.read_len;
+	cutter.m = opt.min_long;
+	cutter.fasta = opt.fasta != 0;
+	const size_t dist_lower_bound = 1000;
+	LengthStats stats;
+	Out out;
+	for (const std::string& path : opt.inputs) {
+		arks_host::SeqReader reader(path, 1u << 22);
 		if (!reader.ok()) {
-			print_error_msg("cannot open " + infile);
+			complain("cannot open " + path);
 			std::exit(EXIT_FAILURE);
 		}
-		arks_host::SeqRecord record;
-		size_t num = 0; // 0-based record index within this file (btllib's record.num)
-		for (; reader.read(record) >= 0; ++num) {
-			const size_t step = l * 2;
-			const std::string& seq = record.seq;
-			const size_t seq_size = seq.size();
-			if (with_bx_multiplicity_only || with_bx_multiplicity) {
-				if (step > seq_size || m > seq_size)
+		arks_host::SeqRecord rec;
+		// num: 0-based record index within this file (btllib's record.num); the barcode is num + 1
+		for (size_t num = 0; reader.read(rec) >= 0; ++num) {
+			const size_t len = rec.seq.size();
+			const bool cut_it = cutter.accepts(len);
+			if (count_bx) {
+				if (!cut_it)
 					continue;
-				if (seq_size % step != 0)
-					bx_multiplicity_ofs << num + 1 << "\t" << (seq_size / step + 1) * 2 << std::endl;
-				else
-					bx_multiplicity_ofs << num + 1 << "\t" << seq_size / l << std::endl;
+				mult_out << num + 1 << "\t" << cutter.multiplicity(len) << std::endl;
+				if (opt.bx_only)
+					continue;
 			}
-			if (with_bx_multiplicity_only)
+			if (opt.want_dist && len > dist_lower_bound)
+				stats.lengths.push_back(len);
+			if (opt.want_span)
+				stats.bases += len;
+			if (!cut_it)
 				continue;
-			if (auto_dist && seq_size > dist_lower_bound)
-				read_lengths.push_back(seq_size);
-			if (auto_span)
-				total_bases += seq_size;
-			if (step > seq_size || m > seq_size)
-				continue;
-
-			cutter.append_pairs(out.buf, record, num);
+			cutter.append_pairs(out.buf, rec, num);
 			out.maybe_flush();
 		}
 	}
 	out.flush();
-
-	if (auto_span || auto_dist) {
-		std::ofstream ofs(configFile, std::ofstream::app);
-		if (auto_span)
-			ofs << "span\t" << (size_t)(total_bases / g * cov_to_span) << "\n";
-		if (auto_dist) {
-			if (read_lengths.size() == 0) {
-				std::cerr << "long-to-linked-pe: unable to estimate dist parameter due to no valid "
-				             "lengths"
-				          << std::endl;
-			} else {
-				size_t dist_estimate;
-				std::sort(read_lengths.begin(), read_lengths.end());
-				double index = (dist_read_perc / 100) * read_lengths.size();
-				size_t size_t_index = (size_t)floor(index);
-				if (floor(index) == index)
-					dist_estimate = (read_lengths[size_t_index - 1] + read_lengths[size_t_index]) / 2;
-				else
-					dist_estimate = read_lengths[size_t_index];
-				ofs << "read_p" << dist_read_perc << "\t" << dist_estimate << "\n";
-			}
-		}
-		ofs.close();
-	}
+	if (opt.want_span || opt.want_dist)
+		stats.write(opt);
 	return 0;
 }

@@ -148,3 +148,34 @@ def test_cut_option_checks_of_the_cli(tmp_path):
     # past the option checks: either it runs (GPU present) or the GPU initialisation fails loudly
     assert "Unknown type file" not in p.stdout and "does not match" not in p.stderr
     assert p.returncode == 0 or "no CPU fallback" in p.stderr
+
+
+def test_span_and_dist_parameters(tmp_path):
+    """-s / -d append `span` and `read_p<P>` to the parameter file (src/long-to-linked-pe.cpp:294-322): span =
+    (total bases / g, integer division) * c; dist = the P-th percentile of the read lengths above 1000, the mean
+    of two neighbours when the rank is whole.  `-t N` also names the parameter file (its case has no break)."""
+    lens = [400, 1200, 1500, 2600, 3000, 5200, 900, 7000]
+    with open(tmp_path / "in.fa", "w") as f:
+        for i, n in enumerate(lens):
+            f.write(">r%d\n%s\n" % (i, "ACGT" * (n // 4)))
+    total = sum(lens)
+    over = sorted(n for n in lens if n > 1000)  # 6 values
+    _run(["-l", "250", "-s", "-g", "1e3", "-c", "0.5", "-d", "-p", "50", "-f", "p.tsv", "in.fa"], tmp_path)
+    rank = 0.5 * len(over)  # 3.0, whole: mean of [2] and [3]
+    assert open(tmp_path / "p.tsv").read() == "span\t%d\nread_p50\t%d\n" % (int(total // 1000 * 0.5), (over[2] + over[3]) // 2)
+    assert rank == int(rank)
+    _run(["-l", "250", "-d", "-p", "70", "-f", "p.tsv", "in.fa"], tmp_path)  # appended; rank 4.2 -> [4]
+    assert open(tmp_path / "p.tsv").read().splitlines()[2] == "read_p70\t%d" % over[4]
+    _run(["-l", "250", "-d", "-t", "3", "in.fa"], tmp_path)  # the parameter file is now called "3"
+    assert open(tmp_path / "3").read() == "read_p50\t%d\n" % ((over[2] + over[3]) // 2)
+    # with --bx the reads that are too short to be cut do not count for -s / -d (the `continue` of :196)
+    _run(["-l", "250", "-s", "-g", "1000", "-d", "--bx", "-b", "m.tsv", "-f", "q.tsv", "in.fa"], tmp_path)
+    kept = [n for n in lens if n >= 2000]
+    k = sorted(kept)
+    r = 0.5 * len(k)
+    want = (k[int(r) - 1] + k[int(r)]) // 2 if r == int(r) else k[int(r)]
+    assert open(tmp_path / "q.tsv").read() == "span\t%d\nread_p50\t%d\n" % (int(sum(kept) // 1000 * 0.25), want)
+    # nothing above 1000 bases: a message instead of an estimate
+    (tmp_path / "short.fa").write_text(">a\nACGT\n")
+    p = subprocess.run([TOOL, "-l", "2", "-m", "0", "-d", "-f", "e.tsv", "short.fa"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert b"unable to estimate dist parameter" in p.stderr
