@@ -55,3 +55,45 @@ def test_cut_long_reads_on_the_fly(argsfile, mode, tmp_path):
     assert read(tmp_path / "o_main.tsv") == read(exp + "_main.tsv")
     assert read(tmp_path / "o_pair.tsv") == read(exp + "_pmap.txt")
     assert read(tmp_path / "bc.tsv") == read(exp + "_bc.tsv")
+
+
+def test_long_read_shaped_pairs_match_oracle():
+    """BASELINE.json's arks-long configuration in small, through the C ABI: pseudo read pairs of 250 bases cut from
+    long reads with 8 % substitutions (so nearly every 20-mer window sits next to an error), k=20, j=0.05, barcode
+    = long read; per-pair contig ends and all counters against the CPU restatement"""
+    import numpy as np
+    from test_gpu_parity import _check_index
+    from tools import synth
+    k, j, L = 20, 0.05, 250
+    rng = np.random.default_rng(4242)
+    genome, contigs = synth.make_draft(rng, 200000, 12000, k, n_runs=6, palindromes=3)
+    bases, end_off, conreci, _ = synth.contig_end_arrays(genome, contigs, k, min_size=500, end_length=30000)
+    idx, km = _check_index(k, bases, end_off, conreci)
+    reads, bc = [], []
+    for i in range(70):
+        n = int(np.clip(rng.lognormal(np.log(8000), 0.6), 2000, 40000))
+        a = int(rng.integers(0, len(genome) - n))
+        r = genome[a:a + n].copy()
+        sub = rng.random(n) < 0.08
+        r[sub] = synth.ACGT[rng.integers(0, 4, int(sub.sum()))]
+        if i % 7 == 0:
+            r[rng.integers(0, n, 3)] = ord("N")
+        if i % 2:
+            r = synth.revcomp(r)
+        step = 2 * L
+        for p in range(0, n - step + 1, step):  # the cutting rule of long-to-linked-pe
+            reads += [r[p:p + L], synth.revcomp(r[p + L:p + step])]
+            bc.append(i)
+        rem = n % step
+        if rem:
+            m = min(L, rem)
+            reads += [r[n - rem:n - rem + m], synth.revcomp(r[n - m:n])]
+            bc.append(i)
+    rb = np.concatenate(reads).astype(np.uint8)
+    roff = np.zeros(len(reads) + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(x) for x in reads])
+    got = idx.map_pairs(rb, roff, np.asarray(bc, dtype=np.uint32), j)
+    want, st = km.map_pairs(rb, roff, j)
+    assert len(bc) > 1000 and (want != 0).sum() > 200
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+    assert idx.map_stats().as_dict() == st.as_dict()
