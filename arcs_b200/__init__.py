@@ -10,9 +10,13 @@ from .api import (  # noqa: F401
     ArksIndex,
     IndexStats,
     MapStats,
+    comm_init_local,
+    comm_unique_id,
     head_tail_table,
     lib_path,
     load_library,
+    merge_pmap_local,
 )
 
-__all__ = ["ArksError", "ArksIndex", "IndexStats", "MapStats", "head_tail_table", "lib_path", "load_library"]
+__all__ = ["ArksError", "ArksIndex", "IndexStats", "MapStats", "head_tail_table", "lib_path", "load_library",
+           "comm_unique_id", "comm_init_local", "merge_pmap_local"]

@@ -50,6 +50,7 @@ SYMBOLS = [
     "arks_index_dump", "arks_set_conreci_remap", "arks_map_pairs", "arks_map_pairs_device", "arks_map_get_stats",
     "arks_map_stats_reset", "arks_imap_size", "arks_imap_export", "arks_imap_add", "arks_pair_links",
     "arks_pmap_size", "arks_pmap_export", "arks_head_tail_table", "arks_launch_count", "arks_device_init",
+    "arks_imap_clear", "arks_bind_thread", "arks_device_numa_node", "arks_map_pairs_begin", "arks_map_pairs_end", "arks_pmap_digest", "arks_comm_unique_id", "arks_comm_init_rank", "arks_comm_init_local", "arks_merge_pmap",
 ]
 
 
@@ -74,6 +75,8 @@ def load_library():
     L.arks_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.arks_host_free.argtypes = [vp]
     L.arks_device_init.argtypes = [C.c_int]
+    L.arks_bind_thread.argtypes = [C.c_int]
+    L.arks_device_numa_node.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.arks_index_add.argtypes = [vp, vp, u64p, u32p, C.c_uint32]
     L.arks_index_add_device.argtypes = [vp, vp, vp, vp, u64p, C.c_uint32]
     L.arks_index_finalize.argtypes = [vp, C.POINTER(IndexStats)]
@@ -81,16 +84,24 @@ def load_library():
     L.arks_index_dump.argtypes = [vp, u8p, i32p, C.c_uint64, u64p]
     L.arks_set_conreci_remap.argtypes = [vp, u32p, C.c_uint32]
     L.arks_map_pairs.argtypes = [vp, vp, u32p, u32p, C.c_uint32, C.c_double, i32p]
+    L.arks_map_pairs_begin.argtypes = [vp, vp, u32p, u32p, C.c_uint32, C.c_double, i32p]
+    L.arks_map_pairs_end.argtypes = [vp]
     L.arks_map_pairs_device.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_double, vp]
     L.arks_map_get_stats.argtypes = [vp, C.POINTER(MapStats)]
     L.arks_map_stats_reset.argtypes = [vp]
     L.arks_imap_size.argtypes = [vp, u64p]
     L.arks_imap_export.argtypes = [vp, u32p, u32p, u32p, u32p, C.c_uint64, u64p]
+    L.arks_imap_clear.argtypes = [vp]
     L.arks_imap_add.argtypes = [vp, u32p, u32p, u32p, u32p, C.c_uint64]
     L.arks_pair_links.argtypes = [vp, i32p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_float, u32p, C.c_uint32]
     L.arks_pmap_size.argtypes = [vp, u64p]
     L.arks_pmap_export.argtypes = [vp, u32p, u32p, u32p, C.c_uint64, u64p]
     L.arks_head_tail_table.argtypes = [C.c_int, C.c_float, C.c_uint32, u32p]
+    L.arks_pmap_digest.argtypes = [vp, u64p]
+    L.arks_comm_unique_id.argtypes = [u8p]
+    L.arks_comm_init_rank.argtypes = [vp, u8p, C.c_int, C.c_int]
+    L.arks_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.arks_merge_pmap.argtypes = [C.POINTER(vp), C.c_int]
     L.arks_launch_count.argtypes = [vp]
     L.arks_launch_count.restype = C.c_uint64
     for name in SYMBOLS:
@@ -221,21 +232,83 @@ class ArksIndex:
             self._ck(self.L.arks_imap_export(self.h, *[_p(x, C.c_uint32) for x in a], n.value, C.byref(n)))
         return a  # barcode, contig, head, tail
 
+    def imap_clear(self):
+        self._ck(self.L.arks_imap_clear(self.h))
+
     def imap_add(self, barcode, contig, head, tail):
         a = [np.ascontiguousarray(x, dtype=np.uint32) for x in (barcode, contig, head, tail)]
         self._ck(self.L.arks_imap_add(self.h, *[_p(x, C.c_uint32) for x in a], len(a[0])))
 
-    def pair_links(self, mult, min_mult, max_mult, min_reads, error_percent, lexrank):
+    def pair_links_run(self, mult, min_mult, max_mult, min_reads, error_percent, lexrank):
+        """pairContigs on the device; the ordered rows stay there (pmap_rows / pmap_digest / merge_pmap)"""
         mult = np.ascontiguousarray(mult, dtype=np.int32)
         lexrank = np.ascontiguousarray(lexrank, dtype=np.uint32)
         self._ck(self.L.arks_pair_links(self.h, _p(mult, C.c_int32), len(mult), min_mult, max_mult, min_reads,
                                         float(error_percent), _p(lexrank, C.c_uint32), len(lexrank)))
+
+    def pmap_size(self):
         n = C.c_uint64()
         self._ck(self.L.arks_pmap_size(self.h, C.byref(n)))
-        a = np.zeros(n.value, dtype=np.uint32)
-        b = np.zeros(n.value, dtype=np.uint32)
-        c = np.zeros((n.value, 4), dtype=np.uint32)
-        if n.value:
-            self._ck(self.L.arks_pmap_export(self.h, _p(a, C.c_uint32), _p(b, C.c_uint32), _p(c, C.c_uint32), n.value,
-                                             C.byref(n)))
+        return int(n.value)
+
+    def pmap_rows(self):
+        n = self.pmap_size()
+        a = np.zeros(n, dtype=np.uint32)
+        b = np.zeros(n, dtype=np.uint32)
+        c = np.zeros((n, 4), dtype=np.uint32)
+        if n:
+            nn = C.c_uint64()
+            self._ck(self.L.arks_pmap_export(self.h, _p(a, C.c_uint32), _p(b, C.c_uint32), _p(c, C.c_uint32), n, C.byref(nn)))
         return a, b, c
+
+    def pmap_export_raw(self, a_ptr, b_ptr, c_ptr, cap):
+        """export into caller-owned host memory (pinned: arks_host_alloc) -> number of rows"""
+        nn = C.c_uint64()
+        u32p = C.POINTER(C.c_uint32)
+        self._ck(self.L.arks_pmap_export(self.h, C.cast(a_ptr, u32p), C.cast(b_ptr, u32p), C.cast(c_ptr, u32p), cap, C.byref(nn)))
+        return int(nn.value)
+
+    def pmap_digest(self):
+        d = (C.c_uint64 * 2)()
+        self._ck(self.L.arks_pmap_digest(self.h, d))
+        return int(d[0]), int(d[1])
+
+    def pair_links(self, mult, min_mult, max_mult, min_reads, error_percent, lexrank):
+        self.pair_links_run(mult, min_mult, max_mult, min_reads, error_percent, lexrank)
+        return self.pmap_rows()
+
+    # ---- multi-GPU (one process per GPU): the single NCCL exchange of the pair-link map
+    def comm_init_rank(self, comm_id, rank, n_ranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(comm_id))
+        self._ck(self.L.arks_comm_init_rank(self.h, buf, rank, n_ranks))
+
+    def merge_pmap(self):
+        hs = (C.c_void_p * 1)(self.h)
+        self._ck(self.L.arks_merge_pmap(hs, 1))
+
+
+def comm_unique_id():
+    """ncclUniqueId (128 bytes) made by this process; hand it to every rank's comm_init_rank"""
+    L = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = L.arks_comm_unique_id(buf)
+    if rc:
+        raise ArksError(rc, L.arks_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_init_local(indexes):
+    """one process, several handles (one per GPU, or several shards on one GPU in tests)"""
+    L = load_library()
+    hs = (C.c_void_p * len(indexes))(*[i.h for i in indexes])
+    rc = L.arks_comm_init_local(hs, len(indexes))
+    if rc:
+        raise ArksError(rc, L.arks_last_error(indexes[0].h).decode())
+
+
+def merge_pmap_local(indexes):
+    L = load_library()
+    hs = (C.c_void_p * len(indexes))(*[i.h for i in indexes])
+    rc = L.arks_merge_pmap(hs, len(indexes))
+    if rc:
+        raise ArksError(rc, L.arks_last_error(indexes[0].h).decode())

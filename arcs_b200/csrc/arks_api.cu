@@ -6,15 +6,18 @@
 #include "arks_index.cuh"
 #include "arks_links.cuh"
 #include "arks_map.cuh"
+#include "arks_nccl.h"
+#include "arks_sort.cuh"
 
 #include <algorithm>
+#include <cctype>
+#include <sched.h>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
-#include <parallel/algorithm>
 #include <string>
 #include <vector>
 
@@ -35,6 +38,8 @@ struct MapSlot
 	DevBuf bases, off, bc, out;
 	cudaEvent_t copied = nullptr, done = nullptr;
 	bool busy = false;
+	bool copy_pending = false; // arks_map_pairs_begin without its arks_map_pairs_end yet
+	bool wants_out = false;
 };
 
 } // namespace
@@ -83,14 +88,23 @@ struct arks_handle
 	uint64_t imap_cap = 0;
 	unsigned long long* d_imap_count = nullptr;
 	uint64_t imap_upper = 0; // host-side upper bound on the number of rows
-	// pmap
-	unsigned long long* pmap = nullptr;
+	// pair links: workspaces (grown on demand, kept between calls), the pmap hash, and the result as
+	// device arrays sorted by (rank a, rank b): keys, counts[4], contig indices a / b
+	DevBuf lk_table, lk_mult, lk_cnt, lk_fill, lk_offs, lk_sums, lk_rank, lk_inv, lk_rows, lk_rowbc;
+	DevBuf st_key[2], st_val[2], st_hist, st_sums; // radix sort
+	DevBuf pmap_buf;
 	uint64_t pmap_cap = 0;
 	unsigned long long* d_pmap_count = nullptr;
-	std::vector<uint32_t> pm_a, pm_b, pm_counts; // sorted host copy
+	DevBuf pm_keys, pm_counts, pm_a, pm_b;
+	uint64_t pm_n = 0;
+	uint32_t pm_n_contigs = 0;
 	bool pmap_ready = false;
+	// multi-GPU merge (arks_merge_pmap): NCCL communicator of this handle, or null
+	void* nccl_comm = nullptr;
+	int comm_rank = 0, comm_size = 1;
+	DevBuf mg_all, mg_dense, mg_head;
 	// misc
-	unsigned long long* d_scratch = nullptr; // 8 x u64 scratch counters
+	unsigned long long* d_scratch = nullptr; // 16 x u64 scratch counters
 	std::string err;
 	uint64_t launches = 0;
 };
@@ -441,6 +455,78 @@ int run_index_add(arks_handle* h, const char* d_bases, const uint64_t* d_end_off
 	return ARKS_OK;
 }
 
+// ---- device radix sort of (key, value) records: arks_sort.cuh -------------------------------------------
+// Sorts the n records in (st_key[0], st_val[0]) by the key bits [lo_bits) of each 32-bit half; returns the
+// index (0/1) of the buffer pair that holds the result.
+int device_sort_pairs(arks_handle* h, uint64_t n, uint32_t half_bits, int* result_buf)
+{
+	*result_buf = 0;
+	if (n < 2)
+		return ARKS_OK;
+	if (n >= 0xFFFFFFFFull)
+		return fail(h, ARKS_E_ARG, "pair-link map too large to sort (>= 2^32 rows)");
+	const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+	const uint64_t n_hist = (uint64_t)kRadix * n_tiles;
+	const uint32_t n_scan_blocks = (uint32_t)((n_hist + kScanBlock - 1) / kScanBlock);
+	int rc;
+	if ((rc = ensure(h, h->st_key[1], n * 8)) || (rc = ensure(h, h->st_val[1], n * 4)) || (rc = ensure(h, h->st_hist, (n_hist + 1) * 4)) ||
+	    (rc = ensure(h, h->st_sums, (uint64_t)n_scan_blocks * 4)))
+		return rc;
+	int cur = 0;
+	for (int half = 0; half < 2; ++half)
+		for (uint32_t s = 0; s < half_bits; s += 8) {
+			const uint32_t shift = 32u * half + s;
+			auto* kin = (unsigned long long*)h->st_key[cur].p;
+			auto* kout = (unsigned long long*)h->st_key[cur ^ 1].p;
+			auto* vin = (uint32_t*)h->st_val[cur].p;
+			auto* vout = (uint32_t*)h->st_val[cur ^ 1].p;
+			auto* hist = (uint32_t*)h->st_hist.p;
+			auto* sums = (uint32_t*)h->st_sums.p;
+			radix_hist_kernel<<<n_tiles, kSortThreads, 0, h->stream>>>(kin, n, shift, hist, n_tiles);
+			scan_block_sums_kernel<<<n_scan_blocks, kScanBlock, 0, h->stream>>>(hist, n_hist, sums);
+			scan_sums_kernel<<<1, kScanBlock, 0, h->stream>>>(sums, n_scan_blocks);
+			scan_apply_kernel<<<n_scan_blocks, kScanBlock, 0, h->stream>>>(hist, n_hist, sums, hist);
+			radix_scatter_kernel<<<n_tiles, kSortThreads, 0, h->stream>>>(kin, vin, kout, vout, n, shift, hist, n_tiles);
+			h->launches += 5;
+			cur ^= 1;
+		}
+	CU(cudaGetLastError());
+	*result_buf = cur;
+	return ARKS_OK;
+}
+
+uint32_t bits_for(uint32_t n)
+{
+	uint32_t b = 1;
+	while (b < 32 && (1ull << b) < n)
+		++b;
+	return b;
+}
+
+void comm_release(arks_handle* h)
+{
+	if (h->nccl_comm && nccl_api().ok)
+		nccl_api().CommDestroy((ncclComm_t)h->nccl_comm);
+	h->nccl_comm = nullptr;
+	h->comm_size = 1;
+	h->comm_rank = 0;
+}
+
+// contig indices of the sorted keys (rank -> first contig of that name)
+int pmap_fill_names(arks_handle* h)
+{
+	int rc;
+	if ((rc = ensure(h, h->pm_a, std::max<uint64_t>(h->pm_n, 1) * 4)) || (rc = ensure(h, h->pm_b, std::max<uint64_t>(h->pm_n, 1) * 4)))
+		return rc;
+	if (h->pm_n) {
+		pmap_names_kernel<<<grid_for(h, h->pm_n, 256, 8), 256, 0, h->stream>>>((const unsigned long long*)h->pm_keys.p, h->pm_n,
+		    (const uint32_t*)h->lk_inv.p, (uint32_t*)h->pm_a.p, (uint32_t*)h->pm_b.p);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	return ARKS_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -544,7 +630,7 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 	CUC(cudaMalloc(&h->d_imap_count, 8));
 	CUC(cudaMemsetAsync(h->d_imap_count, 0, 8, h->stream));
 	CUC(cudaMalloc(&h->d_pmap_count, 8));
-	CUC(cudaMalloc(&h->d_scratch, 64));
+	CUC(cudaMalloc(&h->d_scratch, 128));
 	if (imap_alloc(h, 1ull << 16))
 		return bail(ARKS_E_CUDA);
 	{
@@ -618,8 +704,14 @@ void arks_destroy(arks_handle* h)
 		if (s.done)
 			cudaEventDestroy(s.done);
 	}
+	for (DevBuf* b : {&h->lk_table, &h->lk_mult, &h->lk_cnt, &h->lk_fill, &h->lk_offs, &h->lk_sums, &h->lk_rank, &h->lk_inv, &h->lk_rows,
+	         &h->lk_rowbc, &h->st_key[0], &h->st_key[1], &h->st_val[0], &h->st_val[1], &h->st_hist, &h->st_sums, &h->pmap_buf, &h->pm_keys,
+	         &h->pm_counts, &h->pm_a, &h->pm_b, &h->mg_all, &h->mg_dense, &h->mg_head})
+		if (b->p)
+			cudaFree(b->p);
+	comm_release(h);
 	for (void* p : {(void*)h->table, (void*)h->d_ictr, (void*)h->d_mctr, (void*)h->d_remap, (void*)h->imap, (void*)h->d_imap_count,
-	         (void*)h->pmap, (void*)h->d_pmap_count, (void*)h->d_scratch, (void*)h->d_jmin, (void*)h->d_nmax, (void*)h->d_work_count,
+	         (void*)h->d_pmap_count, (void*)h->d_scratch, (void*)h->d_jmin, (void*)h->d_nmax, (void*)h->d_work_count,
 	         h->work.p, (void*)h->bloom})
 		if (p)
 			cudaFree(p);
@@ -669,6 +761,67 @@ int arks_device_init(int device)
 	arks_handle* h = nullptr;
 	CU(cudaSetDevice(device));
 	CU(cudaFree(0));
+	return ARKS_OK;
+}
+
+// NUMA node of a CUDA device from sysfs (-1 if it cannot be told)
+static int device_numa_node(int device)
+{
+	char bus[32] = {0};
+	if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess)
+		return -1;
+	for (char* c = bus; *c; ++c)
+		*c = (char)tolower((unsigned char)*c);
+	const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+	FILE* f = fopen(path.c_str(), "r");
+	if (!f)
+		return -1;
+	int node = -1;
+	if (fscanf(f, "%d", &node) != 1)
+		node = -1;
+	fclose(f);
+	return node;
+}
+
+int arks_device_numa_node(int device, int* node)
+{
+	if (!node)
+		return ARKS_E_ARG;
+	*node = device_numa_node(device);
+	return ARKS_OK;
+}
+
+int arks_bind_thread(int device)
+{
+	const int node = device_numa_node(device);
+	if (node < 0)
+		return ARKS_OK; // single-node host or unknown topology: nothing to do
+	char path[128];
+	snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+	FILE* f = fopen(path, "r");
+	if (!f)
+		return ARKS_OK;
+	char list[4096] = {0};
+	const bool got = fgets(list, sizeof(list), f) != nullptr;
+	fclose(f);
+	if (!got)
+		return ARKS_OK;
+	cpu_set_t set;
+	CPU_ZERO(&set);
+	int n_set = 0;
+	for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+		int a = 0, b = 0;
+		const int got2 = sscanf(tok, "%d-%d", &a, &b);
+		if (got2 == 1)
+			b = a;
+		if (got2 >= 1)
+			for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+				CPU_SET(c, &set);
+				n_set++;
+			}
+	}
+	if (n_set)
+		sched_setaffinity(0, sizeof(set), &set); // the calling thread; best effort (a cgroup may forbid some cores)
 	return ARKS_OK;
 }
 
@@ -870,6 +1023,33 @@ int arks_set_conreci_remap(arks_handle* h, const uint32_t* remap, uint32_t n)
 int arks_map_pairs(arks_handle* h, const char* bases, const uint32_t* read_off, const uint32_t* barcode_id, uint32_t n_pairs,
     double j_index, int32_t* conreci_out)
 {
+	int rc = arks_map_pairs_begin(h, bases, read_off, barcode_id, n_pairs, j_index, conreci_out);
+	if (rc)
+		return rc;
+	return arks_map_pairs_end(h);
+}
+
+int arks_map_pairs_end(arks_handle* h)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	for (auto& s : h->slots)
+		if (s.copy_pending) {
+			// inputs consumed once the copies have landed; the kernels keep running
+			CU(cudaEventSynchronize(s.copied));
+			s.copy_pending = false;
+			if (s.wants_out) {
+				CU(cudaStreamSynchronize(h->stream));
+				s.wants_out = false;
+			}
+		}
+	return ARKS_OK;
+}
+
+int arks_map_pairs_begin(arks_handle* h, const char* bases, const uint32_t* read_off, const uint32_t* barcode_id, uint32_t n_pairs,
+    double j_index, int32_t* conreci_out)
+{
 	if (!h || !bases || !read_off || !barcode_id)
 		return fail(h, ARKS_E_ARG, "arks_map_pairs: null argument");
 	if (!h->finalized)
@@ -883,6 +1063,10 @@ int arks_map_pairs(arks_handle* h, const char* bases, const uint32_t* read_off, 
 	const uint64_t n_bases = read_off[2ull * n_pairs] - first;
 	MapSlot& s = h->slots[h->next_slot];
 	h->next_slot ^= 1;
+	if (s.copy_pending) { // a begin without its end: its buffers are the caller's business, the slot's are ours
+		CU(cudaEventSynchronize(s.copied));
+		s.copy_pending = false;
+	}
 	if (s.busy) { // the kernel that last read this slot's buffers must be finished
 		CU(cudaEventSynchronize(s.done));
 		s.busy = false;
@@ -908,10 +1092,8 @@ int arks_map_pairs(arks_handle* h, const char* bases, const uint32_t* read_off, 
 		CU(cudaMemcpyAsync(conreci_out, s.out.p, n_pairs * 4ull, cudaMemcpyDeviceToHost, h->stream));
 	CU(cudaEventRecord(s.done, h->stream));
 	s.busy = true;
-	// inputs consumed once the copies have landed; the kernel keeps running
-	CU(cudaEventSynchronize(s.copied));
-	if (conreci_out)
-		CU(cudaStreamSynchronize(h->stream));
+	s.copy_pending = true;
+	s.wants_out = conreci_out != nullptr;
 	return ARKS_OK;
 }
 
@@ -975,6 +1157,20 @@ int arks_imap_size(arks_handle* h, uint64_t* n_rows)
 	CU(cudaMemcpyAsync(&n, h->d_imap_count, 8, cudaMemcpyDeviceToHost, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
 	*n_rows = n;
+	return ARKS_OK;
+}
+
+int arks_imap_clear(arks_handle* h)
+{
+	if (!h)
+		return ARKS_E_ARG;
+	CU(cudaSetDevice(h->device));
+	init_slots_kernel<<<grid_for(h, h->imap_cap * 2, 256, 8), 256, 0, h->stream>>>(h->imap, h->imap_cap * 2, 2);
+	h->launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemsetAsync(h->d_imap_count, 0, 8, h->stream));
+	h->imap_upper = 0;
+	h->pmap_ready = false;
 	return ARKS_OK;
 }
 
@@ -1045,10 +1241,11 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 		return fail(h, ARKS_E_ARG, "arks_pair_links: null argument");
 	CU(cudaSetDevice(h->device));
 	h->pmap_ready = false;
-	h->pm_a.clear();
-	h->pm_b.clear();
-	h->pm_counts.clear();
+	h->pm_n = 0;
 	cudaStream_t st = h->stream;
+	for (uint32_t c = 0; c < n_contigs; ++c)
+		if (lexrank[c] >= n_contigs)
+			return fail(h, ARKS_E_ARG, "arks_pair_links: lexrank must be < n_contigs");
 	// 1. largest head+tail -> decision table
 	uint32_t* d_maxsum = reinterpret_cast<uint32_t*>(h->d_scratch);
 	CU(cudaMemsetAsync(h->d_scratch, 0, 64, st));
@@ -1061,42 +1258,33 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 	int rc = build_ht_table(min_reads, error_percent, maxsum + 1, table.data());
 	if (rc)
 		return fail(h, rc, "head/tail predicate is not monotone in max for this (min_reads, error_percent)");
-	uint32_t *d_table = nullptr, *d_cnt = nullptr, *d_offs = nullptr, *d_fill = nullptr, *d_rows = nullptr, *d_sums = nullptr,
-	         *d_rank = nullptr;
-	int32_t* d_mult = nullptr;
-	auto cleanup = [&]() {
-		for (void* p : {(void*)d_table, (void*)d_cnt, (void*)d_offs, (void*)d_fill, (void*)d_rows, (void*)d_sums, (void*)d_rank, (void*)d_mult})
-			if (p)
-				cudaFree(p);
-	};
-#define CUL(call)                                                                            \
-	do {                                                                                     \
-		cudaError_t e_ = (call);                                                             \
-		if (e_ != cudaSuccess) {                                                             \
-			cleanup();                                                                       \
-			return fail(h, ARKS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-		}                                                                                    \
-	} while (0)
 	const uint32_t nb = std::max<uint32_t>(n_barcodes, 1);
+	const uint32_t nc = std::max<uint32_t>(n_contigs, 1);
 	const uint32_t n_scan_blocks = (nb + kScanBlock - 1) / kScanBlock;
-	CUL(cudaMalloc(&d_table, table.size() * 4));
-	CUL(cudaMalloc(&d_mult, nb * 4ull));
-	CUL(cudaMalloc(&d_cnt, nb * 4ull));
-	CUL(cudaMalloc(&d_fill, nb * 4ull));
-	CUL(cudaMalloc(&d_offs, (nb + 1) * 4ull));
-	CUL(cudaMalloc(&d_sums, n_scan_blocks * 4ull));
-	CUL(cudaMalloc(&d_rank, std::max<uint32_t>(n_contigs, 1) * 4ull));
-	CUL(cudaMemcpyAsync(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st));
-	CUL(cudaMemsetAsync(d_mult, 0, nb * 4ull, st));
+	if ((rc = ensure(h, h->lk_table, table.size() * 4)) || (rc = ensure(h, h->lk_mult, nb * 4ull)) || (rc = ensure(h, h->lk_cnt, nb * 4ull)) ||
+	    (rc = ensure(h, h->lk_fill, nb * 4ull)) || (rc = ensure(h, h->lk_offs, (nb + 1) * 4ull)) ||
+	    (rc = ensure(h, h->lk_sums, n_scan_blocks * 4ull)) || (rc = ensure(h, h->lk_rank, nc * 4ull)) || (rc = ensure(h, h->lk_inv, nc * 4ull)))
+		return rc;
+	uint32_t* d_table = (uint32_t*)h->lk_table.p;
+	int32_t* d_mult = (int32_t*)h->lk_mult.p;
+	uint32_t *d_cnt = (uint32_t*)h->lk_cnt.p, *d_fill = (uint32_t*)h->lk_fill.p, *d_offs = (uint32_t*)h->lk_offs.p,
+	         *d_sums = (uint32_t*)h->lk_sums.p, *d_rank = (uint32_t*)h->lk_rank.p, *d_inv = (uint32_t*)h->lk_inv.p;
+	CU(cudaMemcpyAsync(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(d_mult, 0, nb * 4ull, st));
 	if (n_barcodes)
-		CUL(cudaMemcpyAsync(d_mult, mult, n_barcodes * 4ull, cudaMemcpyHostToDevice, st));
-	if (n_contigs)
-		CUL(cudaMemcpyAsync(d_rank, lexrank, n_contigs * 4ull, cudaMemcpyHostToDevice, st));
-	CUL(cudaMemsetAsync(d_cnt, 0, nb * 4ull, st));
-	CUL(cudaMemsetAsync(d_fill, 0, nb * 4ull, st));
+		CU(cudaMemcpyAsync(d_mult, mult, n_barcodes * 4ull, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(d_inv, 0xFF, nc * 4ull, st));
+	if (n_contigs) {
+		CU(cudaMemcpyAsync(d_rank, lexrank, n_contigs * 4ull, cudaMemcpyHostToDevice, st));
+		rank_inverse_kernel<<<grid_for(h, n_contigs, 256, 8), 256, 0, st>>>(d_rank, n_contigs, d_inv);
+		h->launches++;
+	}
+	h->pm_n_contigs = n_contigs;
+	CU(cudaMemsetAsync(d_cnt, 0, nb * 4ull, st));
+	CU(cudaMemsetAsync(d_fill, 0, nb * 4ull, st));
 	LinkParams L{h->imap, h->imap_cap, d_mult, n_barcodes, min_mult, max_mult, d_table, (uint32_t)table.size()};
 	const int g_imap = grid_for(h, h->imap_cap, 256, 8);
-	// 2. count passing rows per barcode, 3. scan, 4. scatter
+	// 2. count passing rows per barcode, 3. scan, 4. scatter (rows grouped by barcode)
 	imap_count_kernel<<<g_imap, 256, 0, st>>>(L, d_cnt);
 	scan_block_sums_kernel<<<n_scan_blocks, kScanBlock, 0, st>>>(d_cnt, nb, d_sums);
 	scan_sums_kernel<<<1, kScanBlock, 0, st>>>(d_sums, n_scan_blocks);
@@ -1104,81 +1292,81 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 	unsigned long long* d_events = h->d_scratch + 1;
 	pair_count_kernel<<<grid_for(h, nb, 256, 8), 256, 0, st>>>(d_cnt, nb, d_events);
 	h->launches += 5;
-	CUL(cudaGetLastError());
+	CU(cudaGetLastError());
 	uint32_t n_rows = 0;
 	unsigned long long events = 0;
-	CUL(cudaMemcpyAsync(&n_rows, d_offs + nb, 4, cudaMemcpyDeviceToHost, st));
-	CUL(cudaMemcpyAsync(&events, d_events, 8, cudaMemcpyDeviceToHost, st));
-	CUL(cudaStreamSynchronize(st));
-	CUL(cudaMalloc(&d_rows, std::max<uint32_t>(n_rows, 1) * 4ull));
-	imap_scatter_kernel<<<g_imap, 256, 0, st>>>(L, d_offs, d_fill, d_rows);
+	CU(cudaMemcpyAsync(&n_rows, d_offs + nb, 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(&events, d_events, 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if ((rc = ensure(h, h->lk_rows, std::max<uint32_t>(n_rows, 1) * 4ull)) || (rc = ensure(h, h->lk_rowbc, std::max<uint32_t>(n_rows, 1) * 4ull)))
+		return rc;
+	uint32_t *d_rows = (uint32_t*)h->lk_rows.p, *d_rowbc = (uint32_t*)h->lk_rowbc.p;
+	imap_scatter_kernel<<<g_imap, 256, 0, st>>>(L, d_offs, d_fill, d_rows, d_rowbc);
 	h->launches++;
-	// 5. pmap table sized by the number of pair events (an upper bound on distinct pairs)
+	CU(cudaGetLastError());
+	// 5. the pmap hash.  The number of pair events bounds the number of distinct pairs from above, usually by
+	// far (neighbouring contigs share many barcodes), so the table starts at 2 x min(events, all pairs, 2^25) slots
+	// and is doubled -- and the pass repeated -- if it fills up beyond 70 %.
 	unsigned long long bound = events;
-	if (n_contigs) {
-		unsigned long long all = (unsigned long long)n_contigs * (n_contigs - 1) / 2;
-		bound = std::min(bound, all);
-	}
+	if (n_contigs)
+		bound = std::min(bound, (unsigned long long)n_contigs * (n_contigs - 1) / 2);
 	uint64_t cap = 1024;
-	while (cap < bound * 2)
+	while (cap < 2 * std::min<unsigned long long>(bound, 1ull << 25))
 		cap <<= 1;
-	if (h->pmap) {
-		CUL(cudaFree(h->pmap));
-		h->pmap = nullptr;
+	if (const char* e = getenv("ARKS_PMAP_INITIAL_SLOTS")) { // tests: force the growth path
+		cap = 1024;
+		while (cap < (uint64_t)atoll(e))
+			cap <<= 1;
 	}
-	CUL(cudaMalloc(&h->pmap, cap * 32));
-	h->pmap_cap = cap;
-	init_slots_kernel<<<grid_for(h, cap * 4, 256, 8), 256, 0, st>>>(h->pmap, cap * 4, 4);
-	h->launches++;
-	CUL(cudaMemsetAsync(h->d_pmap_count, 0, 8, st));
-	if (events) {
-		pair_kernel<<<grid_for(h, (uint64_t)nb * 32, 256, 8), 256, 0, st>>>(d_offs, d_rows, n_barcodes, d_rank, h->pmap, cap - 1, h->d_pmap_count);
-		h->launches++;
-	}
-	CUL(cudaGetLastError());
-	// 6. export + order by (rank a, rank b) = std::map<pair<string,string>> iteration order
 	unsigned long long n_pairs = 0;
-	CUL(cudaMemcpyAsync(&n_pairs, h->d_pmap_count, 8, cudaMemcpyDeviceToHost, st));
-	CUL(cudaStreamSynchronize(st));
-	if (n_pairs) {
-		uint32_t* d_out = nullptr;
-		CUL(cudaMalloc(&d_out, n_pairs * 24));
-		CUL(cudaMemsetAsync(h->d_scratch, 0, 8, st));
-		pmap_export_kernel<<<grid_for(h, cap, 256, 8), 256, 0, st>>>(h->pmap, cap, d_out, d_out + n_pairs, d_out + 2 * n_pairs, h->d_scratch, n_pairs);
+	uint32_t* d_overflow = reinterpret_cast<uint32_t*>(h->d_scratch + 2);
+	while (true) {
+		if ((rc = ensure(h, h->pmap_buf, cap * 32)))
+			return rc;
+		h->pmap_cap = cap;
+		unsigned long long* pmap = (unsigned long long*)h->pmap_buf.p;
+		init_slots_kernel<<<grid_for(h, cap * 4, 256, 8), 256, 0, st>>>(pmap, cap * 4, 4);
 		h->launches++;
-		std::vector<uint32_t> a(n_pairs), b(n_pairs), c(4 * n_pairs);
-		cudaError_t e1 = cudaMemcpyAsync(a.data(), d_out, n_pairs * 4, cudaMemcpyDeviceToHost, st);
-		cudaError_t e2 = cudaMemcpyAsync(b.data(), d_out + n_pairs, n_pairs * 4, cudaMemcpyDeviceToHost, st);
-		cudaError_t e3 = cudaMemcpyAsync(c.data(), d_out + 2 * n_pairs, n_pairs * 16, cudaMemcpyDeviceToHost, st);
-		cudaError_t e4 = cudaStreamSynchronize(st);
-		cudaFree(d_out);
-		if (e1 || e2 || e3 || e4) {
-			cleanup();
-			return fail(h, ARKS_E_CUDA, "pmap export copy failed");
+		CU(cudaMemsetAsync(h->d_pmap_count, 0, 8, st));
+		CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+		const uint64_t limit = cap >= 2 * bound ? cap : cap / 10 * 7;
+		if (events && n_rows) {
+			pair_kernel<<<grid_for(h, n_rows, 128, 16), 128, 0, st>>>(d_offs, d_rows, d_rowbc, n_rows, d_rank, pmap, cap - 1, h->d_pmap_count,
+			    limit, d_overflow);
+			h->launches++;
 		}
-		// order by (rank a, rank b): multi-threaded host sort of (key, row) records
-		struct KeyRow
-		{
-			uint64_t key;
-			uint64_t row;
-		};
-		std::vector<KeyRow> order(n_pairs);
-#pragma omp parallel for schedule(static)
-		for (long long i = 0; i < (long long)n_pairs; ++i)
-			order[i] = KeyRow{((uint64_t)lexrank[a[i]] << 32) | lexrank[b[i]], (uint64_t)i};
-		__gnu_parallel::sort(order.begin(), order.end(), [](const KeyRow& x, const KeyRow& y) { return x.key < y.key; });
-		h->pm_a.resize(n_pairs);
-		h->pm_b.resize(n_pairs);
-		h->pm_counts.resize(4 * n_pairs);
-#pragma omp parallel for schedule(static)
-		for (long long i = 0; i < (long long)n_pairs; ++i) {
-			h->pm_a[i] = a[order[i].row];
-			h->pm_b[i] = b[order[i].row];
-			memcpy(&h->pm_counts[4 * i], &c[4 * order[i].row], 16);
-		}
+		CU(cudaGetLastError());
+		uint32_t overflow = 0;
+		CU(cudaMemcpyAsync(&n_pairs, h->d_pmap_count, 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		if (!overflow)
+			break;
+		cap <<= 1;
 	}
-	cleanup();
-#undef CUL
+	// 6. order by (rank a, rank b) = std::map<pair<string,string>> iteration order, on the device
+	h->pm_n = n_pairs;
+	const uint64_t n1 = std::max<uint64_t>(n_pairs, 1);
+	if ((rc = ensure(h, h->st_key[0], n1 * 8)) || (rc = ensure(h, h->st_val[0], n1 * 4)) || (rc = ensure(h, h->pm_keys, n1 * 8)) ||
+	    (rc = ensure(h, h->pm_counts, n1 * 16)))
+		return rc;
+	if (n_pairs) {
+		CU(cudaMemsetAsync(h->d_scratch, 0, 8, st));
+		pmap_collect_kernel<<<grid_for(h, cap, 256, 8), 256, 0, st>>>((const unsigned long long*)h->pmap_buf.p, cap,
+		    (unsigned long long*)h->st_key[0].p, (uint32_t*)h->st_val[0].p, h->d_scratch, n_pairs);
+		h->launches++;
+		int buf = 0;
+		if ((rc = device_sort_pairs(h, n_pairs, bits_for(n_contigs), &buf)))
+			return rc;
+		CU(cudaMemcpyAsync(h->pm_keys.p, h->st_key[buf].p, n_pairs * 8, cudaMemcpyDeviceToDevice, st));
+		pmap_gather_counts_kernel<<<grid_for(h, n_pairs, 256, 8), 256, 0, st>>>((const unsigned long long*)h->pmap_buf.p,
+		    (const uint32_t*)h->st_val[buf].p, n_pairs, (uint32_t*)h->pm_counts.p);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	if ((rc = pmap_fill_names(h)))
+		return rc;
+	CU(cudaStreamSynchronize(st));
 	h->pmap_ready = true;
 	return ARKS_OK;
 }
@@ -1189,7 +1377,7 @@ int arks_pmap_size(arks_handle* h, uint64_t* n_rows)
 		return ARKS_E_ARG;
 	if (!h->pmap_ready)
 		return fail(h, ARKS_E_STATE, "arks_pmap_size before arks_pair_links");
-	*n_rows = h->pm_a.size();
+	*n_rows = h->pm_n;
 	return ARKS_OK;
 }
 
@@ -1199,15 +1387,290 @@ int arks_pmap_export(arks_handle* h, uint32_t* a, uint32_t* b, uint32_t* counts4
 		return ARKS_E_ARG;
 	if (!h->pmap_ready)
 		return fail(h, ARKS_E_STATE, "arks_pmap_export before arks_pair_links");
-	const uint64_t n = h->pm_a.size();
+	const uint64_t n = h->pm_n;
 	*n_rows = n;
 	if (cap < n)
 		return fail(h, ARKS_E_ARG, "arks_pmap_export: cap too small");
 	if (n) {
-		memcpy(a, h->pm_a.data(), n * 4);
-		memcpy(b, h->pm_b.data(), n * 4);
-		memcpy(counts4, h->pm_counts.data(), n * 16);
+		CU(cudaSetDevice(h->device));
+		// the rows are already in order on the device: three copies (at PCIe rate when the caller's arrays
+		// come from arks_host_alloc)
+		CU(cudaMemcpyAsync(a, h->pm_a.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaMemcpyAsync(b, h->pm_b.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaMemcpyAsync(counts4, h->pm_counts.p, n * 16, cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
 	}
+	return ARKS_OK;
+}
+
+int arks_pmap_digest(arks_handle* h, uint64_t digest[2])
+{
+	if (!h || !digest)
+		return ARKS_E_ARG;
+	if (!h->pmap_ready)
+		return fail(h, ARKS_E_STATE, "arks_pmap_digest before arks_pair_links");
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemsetAsync(h->d_scratch + 4, 0, 16, h->stream));
+	if (h->pm_n) {
+		pmap_digest_kernel<<<grid_for(h, h->pm_n, 256, 8), 256, 0, h->stream>>>((const unsigned long long*)h->pm_keys.p,
+		    (const uint32_t*)h->pm_counts.p, h->pm_n, h->d_scratch + 4);
+		h->launches++;
+		CU(cudaGetLastError());
+	}
+	unsigned long long d[2];
+	CU(cudaMemcpyAsync(d, h->d_scratch + 4, 16, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	digest[0] = d[0];
+	digest[1] = d[1];
+	return ARKS_OK;
+}
+
+// ---- multi-GPU: one exchange step for the pair-link map ---------------------------------------------
+
+int arks_comm_unique_id(uint8_t id[ARKS_COMM_ID_BYTES])
+{
+	arks_handle* h = nullptr;
+	if (!id)
+		return ARKS_E_ARG;
+	const NcclApi& N = nccl_api();
+	if (!N.ok)
+		return fail(h, ARKS_E_NCCL, N.error);
+	static_assert(sizeof(ncclUniqueId) == ARKS_COMM_ID_BYTES, "ncclUniqueId size");
+	ncclUniqueId uid;
+	ncclResult_t r = N.GetUniqueId(&uid);
+	if (r != ncclSuccess)
+		return fail(h, ARKS_E_NCCL, std::string("ncclGetUniqueId: ") + N.GetErrorString(r));
+	memcpy(id, &uid, sizeof(uid));
+	return ARKS_OK;
+}
+
+int arks_comm_init_rank(arks_handle* h, const uint8_t id[ARKS_COMM_ID_BYTES], int rank, int n_ranks)
+{
+	if (!h || !id || rank < 0 || rank >= n_ranks)
+		return fail(h, ARKS_E_ARG, "arks_comm_init_rank: bad argument");
+	const NcclApi& N = nccl_api();
+	if (!N.ok)
+		return fail(h, ARKS_E_NCCL, N.error);
+	CU(cudaSetDevice(h->device));
+	comm_release(h);
+	ncclUniqueId uid;
+	memcpy(&uid, id, sizeof(uid));
+	ncclComm_t comm = nullptr;
+	ncclResult_t r = N.CommInitRank(&comm, n_ranks, uid, rank);
+	if (r != ncclSuccess)
+		return fail(h, ARKS_E_NCCL, std::string("ncclCommInitRank: ") + N.GetErrorString(r));
+	h->nccl_comm = comm;
+	h->comm_rank = rank;
+	h->comm_size = n_ranks;
+	return ARKS_OK;
+}
+
+int arks_comm_init_local(arks_handle** hs, int n)
+{
+	if (!hs || n < 1)
+		return ARKS_E_ARG;
+	arks_handle* h = hs[0];
+	for (int i = 0; i < n; ++i)
+		if (!hs[i])
+			return fail(h, ARKS_E_ARG, "arks_comm_init_local: null handle");
+	std::vector<int> devs(n);
+	bool distinct = true;
+	for (int i = 0; i < n; ++i) {
+		devs[i] = hs[i]->device;
+		for (int j = 0; j < i; ++j)
+			distinct &= devs[j] != devs[i];
+	}
+	for (int i = 0; i < n; ++i) {
+		comm_release(hs[i]);
+		hs[i]->comm_rank = i;
+		hs[i]->comm_size = n;
+	}
+	if (n == 1 || !distinct)
+		return ARKS_OK; // shards that share a device exchange with device-to-device copies (arks_merge_pmap)
+	const NcclApi& N = nccl_api();
+	if (!N.ok)
+		return fail(h, ARKS_E_NCCL, N.error);
+	std::vector<ncclComm_t> comms(n, nullptr);
+	ncclResult_t r = N.CommInitAll(comms.data(), n, devs.data());
+	if (r != ncclSuccess)
+		return fail(h, ARKS_E_NCCL, std::string("ncclCommInitAll: ") + N.GetErrorString(r));
+	for (int i = 0; i < n; ++i)
+		hs[i]->nccl_comm = comms[i];
+	return ARKS_OK;
+}
+
+// The pair-link maps of barcode-disjoint shards add up key by key.  Every handle ends up with the
+// merged map: all-gather of the sorted keys (sizes first) -> sort + unique of the concatenation = the same sorted
+// union on every rank -> this rank's counters scattered into a dense 4 x n_union vector -> ONE all-reduce (sum,
+// uint32) -> the union and the reduced vector become the handle's map.  Integer sums: the result depends neither
+// on the number of shards nor on arrival order.
+int arks_merge_pmap(arks_handle** hs, int n_local)
+{
+	if (!hs || n_local < 1 || !hs[0])
+		return ARKS_E_ARG;
+	arks_handle* h = hs[0];
+	const int world = h->comm_size;
+	for (int i = 0; i < n_local; ++i) {
+		if (!hs[i] || !hs[i]->pmap_ready)
+			return fail(h, ARKS_E_STATE, "arks_merge_pmap before arks_pair_links");
+		if (hs[i]->comm_size != world || hs[i]->pm_n_contigs != h->pm_n_contigs)
+			return fail(h, ARKS_E_ARG, "arks_merge_pmap: handles of different communicators / contig sets");
+	}
+	if (world == 1)
+		return ARKS_OK;
+	const bool use_nccl = h->nccl_comm != nullptr;
+	if (!use_nccl && n_local != world)
+		return fail(h, ARKS_E_STATE, "arks_merge_pmap: no communicator (arks_comm_init_rank / arks_comm_init_local first)");
+	const NcclApi& N = nccl_api();
+#define NC(call)                                                                                         \
+	do {                                                                                                 \
+		ncclResult_t r_ = (call);                                                                        \
+		if (r_ != ncclSuccess)                                                                           \
+			return fail(h, ARKS_E_NCCL, std::string(#call) + ": " + N.GetErrorString(r_));               \
+	} while (0)
+	// ---- sizes of every rank's map
+	std::vector<unsigned long long> sizes(world, 0);
+	if (n_local == world) {
+		for (int i = 0; i < n_local; ++i)
+			sizes[hs[i]->comm_rank] = hs[i]->pm_n;
+	} else {
+		for (int i = 0; i < n_local; ++i) {
+			arks_handle* g = hs[i];
+			CU(cudaSetDevice(g->device));
+			int rc = ensure(g, g->mg_head, (uint64_t)world * 8);
+			if (rc)
+				return rc;
+			const unsigned long long mine = g->pm_n;
+			CU(cudaMemcpyAsync(g->d_scratch + 3, &mine, 8, cudaMemcpyHostToDevice, g->stream));
+			CU(cudaStreamSynchronize(g->stream)); // `mine` is a stack variable
+		}
+		NC(N.GroupStart());
+		for (int i = 0; i < n_local; ++i)
+			NC(N.AllGather(hs[i]->d_scratch + 3, hs[i]->mg_head.p, 1, ncclUint64, (ncclComm_t)hs[i]->nccl_comm, hs[i]->stream));
+		NC(N.GroupEnd());
+		CU(cudaSetDevice(h->device));
+		CU(cudaMemcpyAsync(sizes.data(), h->mg_head.p, (size_t)world * 8, cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
+	}
+	std::vector<uint64_t> off(world + 1, 0);
+	for (int r = 0; r < world; ++r)
+		off[r + 1] = off[r] + sizes[r];
+	const uint64_t total = off[world];
+	if (total == 0)
+		return ARKS_OK;
+	// ---- all-gather (v) of the sorted keys into the sort buffer of every handle
+	for (int i = 0; i < n_local; ++i) {
+		arks_handle* g = hs[i];
+		CU(cudaSetDevice(g->device));
+		int rc;
+		if ((rc = ensure(g, g->st_key[0], total * 8)) || (rc = ensure(g, g->st_val[0], total * 4)))
+			return rc;
+	}
+	if (use_nccl) {
+		NC(N.GroupStart());
+		for (int i = 0; i < n_local; ++i) {
+			arks_handle* g = hs[i];
+			for (int r = 0; r < world; ++r) {
+				if (!sizes[r])
+					continue;
+				unsigned long long* dst = (unsigned long long*)g->st_key[0].p + off[r];
+				NC(N.Broadcast(r == g->comm_rank ? g->pm_keys.p : (const void*)dst, dst, sizes[r], ncclUint64, r, (ncclComm_t)g->nccl_comm,
+				    g->stream));
+			}
+		}
+		NC(N.GroupEnd());
+	} else {
+		// all shards live in this process on one device: plain device-to-device copies
+		for (int i = 0; i < n_local; ++i)
+			CU(cudaStreamSynchronize(hs[i]->stream));
+		for (int i = 0; i < n_local; ++i) {
+			arks_handle* g = hs[i];
+			CU(cudaSetDevice(g->device));
+			for (int j = 0; j < n_local; ++j) {
+				const int r = hs[j]->comm_rank;
+				if (sizes[r])
+					CU(cudaMemcpyAsync((unsigned long long*)g->st_key[0].p + off[r], hs[j]->pm_keys.p, sizes[r] * 8, cudaMemcpyDeviceToDevice,
+					    g->stream));
+			}
+		}
+	}
+	// ---- the sorted union, identically on every handle
+	std::vector<int> bufs(n_local, 0);
+	for (int i = 0; i < n_local; ++i) {
+		arks_handle* g = hs[i];
+		CU(cudaSetDevice(g->device));
+		int rc;
+		if ((rc = device_sort_pairs(g, total, bits_for(g->pm_n_contigs), &bufs[i])))
+			return rc;
+		const uint32_t n_scan_blocks = (uint32_t)((total + kScanBlock - 1) / kScanBlock);
+		if ((rc = ensure(g, g->mg_head, (total + 1) * 4)) || (rc = ensure(g, g->st_sums, (uint64_t)n_scan_blocks * 4)) ||
+		    (rc = ensure(g, g->mg_all, total * 8)))
+			return rc;
+		const unsigned long long* sorted = (const unsigned long long*)g->st_key[bufs[i]].p;
+		uint32_t* head = (uint32_t*)g->mg_head.p;
+		run_heads_kernel<<<grid_for(g, total, 256, 8), 256, 0, g->stream>>>(sorted, total, head);
+		scan_block_sums_kernel<<<n_scan_blocks, kScanBlock, 0, g->stream>>>(head, total, (uint32_t*)g->st_sums.p);
+		scan_sums_kernel<<<1, kScanBlock, 0, g->stream>>>((uint32_t*)g->st_sums.p, n_scan_blocks);
+		scan_apply_kernel<<<n_scan_blocks, kScanBlock, 0, g->stream>>>(head, total, (const uint32_t*)g->st_sums.p, head);
+		compact_unique_kernel<<<grid_for(g, total, 256, 8), 256, 0, g->stream>>>(sorted, total, head, (unsigned long long*)g->mg_all.p);
+		g->launches += 5;
+		CU(cudaGetLastError());
+	}
+	uint32_t n_uni = 0;
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemcpyAsync(&n_uni, (uint32_t*)h->mg_head.p + total, 4, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	// ---- dense counter vector, one all-reduce
+	for (int i = 0; i < n_local; ++i) {
+		arks_handle* g = hs[i];
+		CU(cudaSetDevice(g->device));
+		int rc;
+		if ((rc = ensure(g, g->mg_dense, (uint64_t)n_uni * 16)))
+			return rc;
+		CU(cudaMemsetAsync(g->mg_dense.p, 0, (uint64_t)n_uni * 16, g->stream));
+		if (g->pm_n) {
+			scatter_counts_kernel<<<grid_for(g, g->pm_n, 256, 8), 256, 0, g->stream>>>((const unsigned long long*)g->pm_keys.p,
+			    (const uint32_t*)g->pm_counts.p, g->pm_n, (const unsigned long long*)g->mg_all.p, n_uni, (uint32_t*)g->mg_dense.p);
+			g->launches++;
+			CU(cudaGetLastError());
+		}
+	}
+	if (use_nccl) {
+		NC(N.GroupStart());
+		for (int i = 0; i < n_local; ++i)
+			NC(N.AllReduce(hs[i]->mg_dense.p, hs[i]->mg_dense.p, (size_t)n_uni * 4, ncclUint32, ncclSum, (ncclComm_t)hs[i]->nccl_comm,
+			    hs[i]->stream));
+		NC(N.GroupEnd());
+	} else {
+		for (int i = 0; i < n_local; ++i)
+			CU(cudaStreamSynchronize(hs[i]->stream));
+		CU(cudaSetDevice(h->device));
+		for (int j = 1; j < n_local; ++j) {
+			add_u32_kernel<<<grid_for(h, (uint64_t)n_uni * 4, 256, 8), 256, 0, h->stream>>>((uint32_t*)h->mg_dense.p,
+			    (const uint32_t*)hs[j]->mg_dense.p, (uint64_t)n_uni * 4);
+			h->launches++;
+		}
+		CU(cudaGetLastError());
+		CU(cudaStreamSynchronize(h->stream));
+		for (int j = 1; j < n_local; ++j)
+			CU(cudaMemcpyAsync(hs[j]->mg_dense.p, h->mg_dense.p, (uint64_t)n_uni * 16, cudaMemcpyDeviceToDevice, hs[j]->stream));
+	}
+	// ---- the union and the reduced vector become every handle's map
+	for (int i = 0; i < n_local; ++i) {
+		arks_handle* g = hs[i];
+		CU(cudaSetDevice(g->device));
+		std::swap(g->pm_keys, g->mg_all);
+		std::swap(g->pm_counts, g->mg_dense);
+		g->pm_n = n_uni;
+		int rc = pmap_fill_names(g);
+		if (rc)
+			return rc;
+	}
+	for (int i = 0; i < n_local; ++i) {
+		CU(cudaSetDevice(hs[i]->device));
+		CU(cudaStreamSynchronize(hs[i]->stream));
+	}
+#undef NC
 	return ARKS_OK;
 }
 

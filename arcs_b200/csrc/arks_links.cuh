@@ -10,15 +10,19 @@
 //   imap_maxsum_kernel    largest head+tail (sizes the decision table)
 //   imap_count_kernel     per barcode: number of contigs whose head/tail test passes and
 //                         whose barcode multiplicity is inside [min_mult, max_mult]
-//   scan_*                exclusive prefix sum over barcodes (hand-written, 3 phases)
+//   scan_*                exclusive prefix sum over barcodes (arks_sort.cuh)
 //   imap_scatter_kernel   counting-sort the passing rows by barcode
-//   pair_kernel           one warp per barcode: all contig pairs, ordered by the
-//                         host-supplied std::string rank, orientation index
-//                         2*(!Ahead)+(!Bhead) (:1418-1428), accumulated into the pmap
-//                         hash {a<<32|b -> counts[4]}
+//   pair_kernel           one thread per row: the row against the later rows of its barcode,
+//                         contigs ordered by the host-supplied std::string rank, orientation
+//                         index 2*(!Ahead)+(!Bhead) (:1418-1428), accumulated into the pmap
+//                         hash {rank a << 32 | rank b -> counts[4]}
+//   pmap_collect_kernel   occupied slots -> (key, slot) records
+//   radix sort            (arks_sort.cuh) by key = std::map<pair<string,string>> iteration order
+//   pmap_gather_counts_kernel / pmap_names_kernel   sorted rows, ready for one device->host copy
 #pragma once
 #include "arks_device.cuh"
 #include "arks_map.cuh"
+#include "arks_sort.cuh"
 
 namespace arks {
 
@@ -92,7 +96,7 @@ __global__ void imap_count_kernel(LinkParams L, uint32_t* cnt)
 	}
 }
 
-__global__ void imap_scatter_kernel(LinkParams L, const uint32_t* offs, uint32_t* fill, uint32_t* rows)
+__global__ void imap_scatter_kernel(LinkParams L, const uint32_t* offs, uint32_t* fill, uint32_t* rows, uint32_t* row_bc)
 {
 	for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < L.imap_cap; s += (uint64_t)gridDim.x * blockDim.x) {
 		unsigned long long key = L.imap[2 * s];
@@ -100,81 +104,12 @@ __global__ void imap_scatter_kernel(LinkParams L, const uint32_t* offs, uint32_t
 			continue;
 		uint32_t b, packed;
 		if (row_passes(L, key, L.imap[2 * s + 1], b, packed))
-			rows[offs[b] + atomicAdd(&fill[b], 1u)] = packed;
-	}
-}
-
-// ---- exclusive scan of uint32 (n up to 2^32-1), three phases -----------------------------
-constexpr int kScanBlock = 1024;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total)
-{
-	__shared__ uint32_t warp_sums[32];
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t inc = v;
-	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-		if (lane >= (uint32_t)o)
-			inc += t;
-	}
-	if (lane == 31)
-		warp_sums[warp] = inc;
-	__syncthreads();
-	if (warp == 0) {
-		uint32_t ws = warp_sums[lane];
-		uint32_t winc = ws;
-		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, o);
-			if (lane >= (uint32_t)o)
-				winc += t;
+		{
+			const uint32_t at = offs[b] + atomicAdd(&fill[b], 1u);
+			rows[at] = packed;
+			row_bc[at] = b;
 		}
-		warp_sums[lane] = winc - ws; // exclusive
-		if (lane == 31)
-			*total = winc;
 	}
-	__syncthreads();
-	uint32_t r = inc - v + warp_sums[warp];
-	__syncthreads();
-	return r;
-}
-
-__global__ void __launch_bounds__(kScanBlock) scan_block_sums_kernel(const uint32_t* in, uint64_t n, uint32_t* block_sums)
-{
-	__shared__ uint32_t total;
-	uint64_t i = blockIdx.x * (uint64_t)kScanBlock + threadIdx.x;
-	block_exclusive_scan(i < n ? in[i] : 0u, &total);
-	if (threadIdx.x == 0)
-		block_sums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of block_sums in place
-__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks)
-{
-	__shared__ uint32_t total;
-	uint32_t carry = 0;
-	for (uint32_t base = 0; base < n_blocks; base += kScanBlock) {
-		uint32_t i = base + threadIdx.x;
-		uint32_t v = i < n_blocks ? block_sums[i] : 0u;
-		uint32_t ex = block_exclusive_scan(v, &total);
-		if (i < n_blocks)
-			block_sums[i] = ex + carry;
-		carry += total;
-		__syncthreads();
-	}
-}
-
-// out[i] = exclusive prefix; out[n] = grand total
-__global__ void __launch_bounds__(kScanBlock)
-scan_apply_kernel(const uint32_t* in, uint64_t n, const uint32_t* block_sums, uint32_t* out)
-{
-	__shared__ uint32_t total;
-	uint64_t i = blockIdx.x * (uint64_t)kScanBlock + threadIdx.x;
-	uint32_t v = i < n ? in[i] : 0u;
-	uint32_t ex = block_exclusive_scan(v, &total) + block_sums[blockIdx.x];
-	if (i < n)
-		out[i] = ex;
-	if (i == n - 1)
-		out[n] = ex + v;
 }
 
 __global__ void pair_count_kernel(const uint32_t* cnt, uint32_t n_barcodes, unsigned long long* events)
@@ -190,15 +125,18 @@ __global__ void pair_count_kernel(const uint32_t* cnt, uint32_t n_barcodes, unsi
 		atomicAdd(events, e);
 }
 
-// pmap slot: 32 B = {u64 key = a<<32|b, u32 counts[4], u64 pad}
-__device__ __forceinline__ void pmap_add(unsigned long long* pmap, uint64_t mask, unsigned long long* count, uint32_t a, uint32_t b, uint32_t orient)
+// pmap slot: 32 B = {u64 key = rank a << 32 | rank b, u32 counts[4], u64 pad}.  Returns false when the table has
+// reached its fill limit (the host then doubles it and runs the pass again).
+__device__ __forceinline__ bool pmap_add(unsigned long long* pmap, uint64_t mask, unsigned long long* count, uint64_t limit,
+    unsigned long long key, uint32_t orient)
 {
-	unsigned long long key = ((unsigned long long)a << 32) | b;
 	uint64_t slot = mix64(key) & mask;
 	while (true) {
 		unsigned long long* p = pmap + 4 * slot;
 		unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(p);
 		if (cur == kEmptyKey) {
+			if (*reinterpret_cast<volatile unsigned long long*>(count) >= limit)
+				return false;
 			cur = atomicCAS(p, (unsigned long long)kEmptyKey, key);
 			if (cur == kEmptyKey) {
 				atomicAdd(count, 1ull);
@@ -207,57 +145,111 @@ __device__ __forceinline__ void pmap_add(unsigned long long* pmap, uint64_t mask
 		}
 		if (cur == key) {
 			atomicAdd(reinterpret_cast<uint32_t*>(p + 1) + orient, 1u);
-			return;
+			return true;
 		}
 		slot = (slot + 1) & mask;
 	}
 }
 
-__global__ void pair_kernel(const uint32_t* offs, const uint32_t* rows, uint32_t n_barcodes, const uint32_t* rank,
-    unsigned long long* pmap, uint64_t pmap_mask, unsigned long long* pmap_count)
+// rows sorted by barcode (offs = first row of every barcode, row_bc = barcode of every row): one THREAD per
+// row i pairs it with the later rows of its barcode, so a barcode with many contigs is spread over as many
+// threads as it has rows.  Contigs are ordered by the host-supplied std::string rank (Arcs.cpp:1403); the
+// orientation index is 2*(!Ahead)+(!Bhead) (:1418-1428).
+__global__ void pair_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ row_bc,
+    uint32_t n_rows, const uint32_t* __restrict__ rank, unsigned long long* pmap, uint64_t pmap_mask, unsigned long long* pmap_count,
+    uint64_t limit, uint32_t* overflow)
 {
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t bc = gwarp; bc < n_barcodes; bc += nwarps) {
-		const uint32_t r0 = offs[bc], r1 = offs[bc + 1];
-		for (uint32_t i = r0; i + 1 < r1; ++i) {
-			const uint32_t ri = rows[i];
-			const uint32_t ci = ri & 0x7FFFFFFFu, hi = ri >> 31;
-			const uint32_t rki = rank[ci];
-			for (uint32_t j = i + 1 + lane; j < r1; j += 32) {
-				const uint32_t rj = rows[j];
-				const uint32_t cj = rj & 0x7FFFFFFFu, hj = rj >> 31;
-				const uint32_t rkj = rank[cj];
-				if (rki == rkj)
-					continue;
-				const bool i_first = rki < rkj;
-				const uint32_t a = i_first ? ci : cj, b = i_first ? cj : ci;
-				const uint32_t ah = i_first ? hi : hj, bh = i_first ? hj : hi;
-				pmap_add(pmap, pmap_mask, pmap_count, a, b, (ah ? 0u : 2u) + (bh ? 0u : 1u));
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
+		const uint32_t r1 = offs[row_bc[i] + 1];
+		const uint32_t ri = rows[i];
+		const uint32_t hi = ri >> 31;
+		const uint32_t rki = rank[ri & 0x7FFFFFFFu];
+		for (uint32_t j = i + 1; j < r1; ++j) {
+			const uint32_t rj = rows[j];
+			const uint32_t hj = rj >> 31;
+			const uint32_t rkj = rank[rj & 0x7FFFFFFFu];
+			if (rki == rkj)
+				continue;
+			const bool i_first = rki < rkj;
+			const unsigned long long key = i_first ? ((unsigned long long)rki << 32) | rkj : ((unsigned long long)rkj << 32) | rki;
+			const uint32_t ah = i_first ? hi : hj, bh = i_first ? hj : hi;
+			if (!pmap_add(pmap, pmap_mask, pmap_count, limit, key, (ah ? 0u : 2u) + (bh ? 0u : 1u))) {
+				*overflow = 1u;
+				return;
 			}
 		}
 	}
 }
 
-__global__ void pmap_export_kernel(const unsigned long long* pmap, uint64_t cap, uint32_t* a, uint32_t* b, uint32_t* counts,
-    unsigned long long* counter, uint64_t out_cap)
+// occupied slots -> (key, slot index) records, arbitrary order
+__global__ void pmap_collect_kernel(const unsigned long long* __restrict__ pmap, uint64_t cap, unsigned long long* __restrict__ keys,
+    uint32_t* __restrict__ slots, unsigned long long* counter, uint64_t out_cap)
 {
 	for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
-		unsigned long long key = pmap[4 * s];
+		const unsigned long long key = pmap[4 * s];
 		if (key == kEmptyKey)
 			continue;
-		unsigned long long i = atomicAdd(counter, 1ull);
+		const unsigned long long i = atomicAdd(counter, 1ull);
 		if (i < out_cap) {
-			a[i] = (uint32_t)(key >> 32);
-			b[i] = (uint32_t)key;
-			const uint32_t* c = reinterpret_cast<const uint32_t*>(pmap + 4 * s + 1);
-			counts[4 * i + 0] = c[0];
-			counts[4 * i + 1] = c[1];
-			counts[4 * i + 2] = c[2];
-			counts[4 * i + 3] = c[3];
+			keys[i] = key;
+			slots[i] = (uint32_t)s;
 		}
 	}
+}
+
+// counts of the sorted records, gathered from their slots
+__global__ void pmap_gather_counts_kernel(const unsigned long long* __restrict__ pmap, const uint32_t* __restrict__ slots, uint64_t n,
+    uint32_t* __restrict__ counts)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		reinterpret_cast<uint4*>(counts)[i] = *reinterpret_cast<const uint4*>(pmap + 4 * (uint64_t)slots[i] + 1);
+}
+
+// inv[rank[c]] = smallest contig index with that rank (contigs that share a name share a rank, and their
+// hits are tallied under the first of them)
+__global__ void rank_inverse_kernel(const uint32_t* __restrict__ rank, uint32_t n_contigs, uint32_t* __restrict__ inv)
+{
+	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_contigs; c += gridDim.x * blockDim.x)
+		atomicMin(&inv[rank[c]], c);
+}
+
+// sorted keys -> contig indices of the two ends of every link
+__global__ void pmap_names_kernel(const unsigned long long* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ inv,
+    uint32_t* __restrict__ a, uint32_t* __restrict__ b)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const unsigned long long key = keys[i];
+		a[i] = inv[(uint32_t)(key >> 32)];
+		b[i] = inv[(uint32_t)key];
+	}
+}
+
+// order-independent digest of the sorted map (for N-GPU invariance checks): digest[0] = sum of a 64-bit mix of
+// every (key, counts) row, digest[1] = number of rows << 40 + sum of all counters
+__global__ void pmap_digest_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n,
+    unsigned long long* digest)
+{
+	unsigned long long d0 = 0, d1 = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint4 c = reinterpret_cast<const uint4*>(counts)[i];
+		const unsigned long long lo = ((unsigned long long)c.y << 32) | c.x, hi = ((unsigned long long)c.w << 32) | c.z;
+		d0 += mix64(keys[i] ^ mix64(lo + 0x9E3779B97F4A7C15ull) ^ (mix64(hi + 0xC2B2AE3D27D4EB4Full) << 1));
+		d1 += (1ull << 40) + c.x + c.y + c.z + c.w;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		d0 += __shfl_down_sync(0xFFFFFFFFu, d0, o);
+		d1 += __shfl_down_sync(0xFFFFFFFFu, d1, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(digest, d0);
+		atomicAdd(digest + 1, d1);
+	}
+}
+
+__global__ void add_u32_kernel(uint32_t* __restrict__ acc, const uint32_t* __restrict__ x, uint64_t n)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		acc[i] += x[i];
 }
 
 __global__ void imap_export_kernel(const unsigned long long* imap, uint64_t cap, uint32_t* barcode, uint32_t* contig,

@@ -342,6 +342,15 @@ uint64_t g_pair_seq = 0;
 constexpr uint64_t kBatchBases = 256ull << 20;
 constexpr uint32_t kBatchPairs = 1u << 20;
 
+// Multi-GPU hosts: the thread that feeds GPU d (and the pinned buffers it touches first) should live on the
+// NUMA node the GPU hangs off.  arks_bind_thread pins the calling thread to that node's cores; it does nothing
+// on single-node hosts or when the topology cannot be read.
+void bind_thread_to_gpu(int d)
+{
+	if (params.gpus > 1 && !getenv("ARKS_NO_BIND") && !getenv("ARKS_GPUS_SAME_DEVICE"))
+		arks_bind_thread(d);
+}
+
 void ck(arks_handle* h, int rc, const char* what)
 {
 	if (rc != ARKS_OK) {
@@ -1064,6 +1073,10 @@ int main(int argc, char** argv)
 	}
 	if (params.gpus < 1)
 		params.gpus = 1;
+	if (params.gpus > (int)arks_host::kMaxShards) {
+		std::cerr << PROGRAM ": error: --gpus must be at most " << arks_host::kMaxShards << ".\n";
+		exit(EXIT_FAILURE);
+	}
 	printf("%s\n", "Finished reading user inputs...entering runArcs()...");
 
 	// ---- runArcs banner (Arcs.cpp:1818-1843)
@@ -1204,19 +1217,7 @@ int main(int argc, char** argv)
 	gpu_init.join();
 	arks_index_stats ist{};
 	t_index0 = now();
-	for (int d = 0; d < params.gpus; ++d) {
-		Gpu& g = gpus[d];
-		// ARKS_GPUS_SAME_DEVICE=1 (tests): every shard on device 0
-		const int dev = getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d;
-		const double tc0 = now();
-		int rc = arks_create(dev, params.k_value, end_bases.size() + 64, &g.h);
-		t_gpu_init += now() - tc0;
-		if (rc != ARKS_OK)
-			die(std::string("error: cannot initialise GPU ") + std::to_string(d) + ": " + arks_last_error(nullptr));
-		if (!end_conreci.empty())
-			ck(g.h, arks_index_add(g.h, end_bases.data(), end_off.data(), end_conreci.data(), (uint32_t)end_conreci.size()),
-			    "arks_index_add");
-		ck(g.h, arks_index_finalize(g.h, &ist), "arks_index_finalize");
+	{
 		// hits on a contig whose name occurred earlier are tallied under the first one (imap is keyed by name)
 		std::vector<uint32_t> remap(2 * ct.name.size() + 1, 0);
 		bool any = false;
@@ -1225,8 +1226,34 @@ int main(int argc, char** argv)
 			remap[2 * i + 2] = 2 * ct.first_of_name[i] + 2;
 			any |= ct.first_of_name[i] != i;
 		}
-		if (any)
-			ck(g.h, arks_set_conreci_remap(g.h, remap.data(), (uint32_t)remap.size()), "arks_set_conreci_remap");
+		// every GPU builds the same index from the same host buffers, all at once: one host thread per GPU
+		std::vector<arks_index_stats> ists(params.gpus);
+		std::vector<double> t_create(params.gpus, 0.0);
+		auto build = [&](int d) {
+			Gpu& g = gpus[d];
+			bind_thread_to_gpu(d);
+			// ARKS_GPUS_SAME_DEVICE=1 (tests): every shard on device 0
+			const int dev = getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d;
+			const double tc0 = now();
+			int rc = arks_create(dev, params.k_value, end_bases.size() + 64, &g.h);
+			t_create[d] = now() - tc0;
+			if (rc != ARKS_OK)
+				die(std::string("error: cannot initialise GPU ") + std::to_string(d) + ": " + arks_last_error(nullptr));
+			if (!end_conreci.empty())
+				ck(g.h, arks_index_add(g.h, end_bases.data(), end_off.data(), end_conreci.data(), (uint32_t)end_conreci.size()),
+				    "arks_index_add");
+			ck(g.h, arks_index_finalize(g.h, &ists[d]), "arks_index_finalize");
+			if (any)
+				ck(g.h, arks_set_conreci_remap(g.h, remap.data(), (uint32_t)remap.size()), "arks_set_conreci_remap");
+		};
+		std::vector<std::thread> th;
+		for (int d = 1; d < params.gpus; ++d)
+			th.emplace_back(build, d);
+		build(0);
+		for (auto& t : th)
+			t.join();
+		ist = ists[0];
+		t_gpu_init = *std::max_element(t_create.begin(), t_create.end());
 	}
 	t_index1 = now();
 	end_bases.clear();
@@ -1253,17 +1280,21 @@ int main(int argc, char** argv)
 		cfg.max_mult = params.max_mult;
 		arks_host::IngestCounters ictr;
 		arks_host::PairSink sink;
+		cfg.shards = (uint32_t)params.gpus;
 		sink.add = [&](const std::string& s1, const std::string& s2, uint32_t id) {
-			add_pair(gpus[id % params.gpus], s1.data(), s1.size(), s2.data(), s2.size(), id);
+			const std::string& name = bc.name[id];
+			add_pair(gpus[arks_host::barcode_shard(name.data(), name.size(), cfg.shards)], s1.data(), s1.size(), s2.data(), s2.size(), id);
 		};
 		sink.submit = [&](const arks_host::PairBatch& b) {
-			if (params.gpus == 1) { // the block is already a batch in pinned memory
-				ck(gpus[0].h, arks_map_pairs(gpus[0].h, b.bases, b.off, b.bc, b.n_pairs, params.j_index, nullptr), "arks_map_pairs");
-				return;
-			}
-			for (uint32_t i = 0; i < b.n_pairs; ++i)
-				add_pair(gpus[b.bc[i] % params.gpus], b.bases + b.off[2 * i], b.off[2 * i + 1] - b.off[2 * i], b.bases + b.off[2 * i + 1],
-				    b.off[2 * i + 2] - b.off[2 * i + 1], b.bc[i]);
+			// the block is already a batch in pinned memory, laid out by shard: every GPU gets its part with one
+			// asynchronous call, then the copies of all of them are awaited together
+			for (uint32_t g = 0; g < b.n_shards; ++g)
+				if (b.shard_pairs(g))
+					ck(gpus[g].h, arks_map_pairs_begin(gpus[g].h, b.bases, b.shard_off(g), b.shard_bc(g), b.shard_pairs(g), params.j_index, nullptr),
+					    "arks_map_pairs");
+			for (uint32_t g = 0; g < b.n_shards; ++g)
+				if (b.shard_pairs(g))
+					ck(gpus[g].h, arks_map_pairs_end(gpus[g].h), "arks_map_pairs");
 		};
 		// block-parallel parsing (ingest.h) unless -D needs the pairs' input order or ARKS_PARSE_THREADS=0
 		arks_host::ParallelIngestOptions popt;
@@ -1283,7 +1314,7 @@ int main(int argc, char** argv)
 					die("error: cannot allocate pinned host memory");
 				pb.bases = (char*)p;
 				pinned.push_back(p);
-				if (arks_host_alloc(&p, (2ull * cap_pairs + 1) * 4) != ARKS_OK)
+				if (arks_host_alloc(&p, (2ull * cap_pairs + 1 + arks_host::kMaxShards) * 4) != ARKS_OK)
 					die("error: cannot allocate pinned host memory");
 				pb.off = (uint32_t*)p;
 				pinned.push_back(p);
@@ -1388,45 +1419,67 @@ int main(int argc, char** argv)
 	std::vector<PairRow> pmap;
 	// imap rows (for the TSV): barcode, contig, head, tail
 	std::vector<uint32_t> im_bc, im_ct, im_h, im_t;
-	for (int d = 0; d < params.gpus; ++d) {
-		Gpu& g = gpus[d];
-		uint64_t n_rows = 0;
-		ck(g.h, arks_imap_size(g.h, &n_rows), "arks_imap_size");
-		const size_t base = im_bc.size();
-		im_bc.resize(base + n_rows);
-		im_ct.resize(base + n_rows);
-		im_h.resize(base + n_rows);
-		im_t.resize(base + n_rows);
-		if (n_rows)
-			ck(g.h, arks_imap_export(g.h, im_bc.data() + base, im_ct.data() + base, im_h.data() + base, im_t.data() + base, n_rows, &n_rows),
-			    "arks_imap_export");
-		ck(g.h, arks_pair_links(g.h, mult.data(), n_bc, params.min_mult, params.max_mult, params.min_reads, params.error_percent,
-		            lexrank.data(), n_ct),
-		    "arks_pair_links");
+	const double t_links0 = now();
+	{
+		// every GPU pairs the contigs of ITS barcodes (one host thread per GPU) ...
+		std::vector<uint64_t> im_n(params.gpus, 0);
+		std::vector<std::vector<uint32_t>> im(4 * (size_t)params.gpus);
+		auto links = [&](int d) {
+			Gpu& g = gpus[d];
+			bind_thread_to_gpu(d);
+			uint64_t n_rows = 0;
+			ck(g.h, arks_imap_size(g.h, &n_rows), "arks_imap_size");
+			for (int q = 0; q < 4; ++q)
+				im[4 * d + q].resize(n_rows);
+			if (n_rows)
+				ck(g.h, arks_imap_export(g.h, im[4 * d].data(), im[4 * d + 1].data(), im[4 * d + 2].data(), im[4 * d + 3].data(), n_rows, &n_rows),
+				    "arks_imap_export");
+			im_n[d] = n_rows;
+			ck(g.h, arks_pair_links(g.h, mult.data(), n_bc, params.min_mult, params.max_mult, params.min_reads, params.error_percent,
+			            lexrank.data(), n_ct),
+			    "arks_pair_links");
+		};
+		std::vector<std::thread> th;
+		for (int d = 1; d < params.gpus; ++d)
+			th.emplace_back(links, d);
+		links(0);
+		for (auto& t : th)
+			t.join();
+		for (int d = 0; d < params.gpus; ++d) {
+			im_bc.insert(im_bc.end(), im[4 * d].begin(), im[4 * d].end());
+			im_ct.insert(im_ct.end(), im[4 * d + 1].begin(), im[4 * d + 1].end());
+			im_h.insert(im_h.end(), im[4 * d + 2].begin(), im[4 * d + 2].end());
+			im_t.insert(im_t.end(), im[4 * d + 3].begin(), im[4 * d + 3].end());
+		}
+	}
+	const double t_links1 = now();
+	if (params.gpus > 1) {
+		// ... and since barcodes are disjoint across GPUs the link maps add up key by key: one exchange over
+		// NCCL (all-gather of the sorted keys, one all-reduce of the dense counters), after which GPU 0 holds the sum
+		std::vector<arks_handle*> hs;
+		for (auto& g : gpus)
+			hs.push_back(g.h);
+		ck(hs[0], arks_comm_init_local(hs.data(), params.gpus), "arks_comm_init_local");
+		ck(hs[0], arks_merge_pmap(hs.data(), params.gpus), "arks_merge_pmap");
+	}
+	const double t_merge1 = now();
+	{
+		Gpu& g = gpus[0];
 		uint64_t n = 0;
 		ck(g.h, arks_pmap_size(g.h, &n), "arks_pmap_size");
-		std::vector<uint32_t> a(n), b(n), c(4 * n);
-		if (n)
-			ck(g.h, arks_pmap_export(g.h, a.data(), b.data(), c.data(), n, &n), "arks_pmap_export");
-		for (uint64_t i = 0; i < n; ++i)
-			pmap.push_back(PairRow{ a[i], b[i], { c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3] } });
-	}
-	if (params.gpus > 1) {
-		// barcodes are disjoint across GPUs, so the link maps simply add up
-		std::sort(pmap.begin(), pmap.end(), [&](const PairRow& x, const PairRow& y) {
-			return std::make_pair(lexrank[x.a], lexrank[x.b]) < std::make_pair(lexrank[y.a], lexrank[y.b]);
-		});
-		size_t w = 0;
-		for (size_t i = 0; i < pmap.size(); ++i) {
-			if (w && pmap[w - 1].a == pmap[i].a && pmap[w - 1].b == pmap[i].b) {
-				for (int o = 0; o < 4; ++o)
-					pmap[w - 1].c[o] += pmap[i].c[o];
-			} else {
-				pmap[w++] = pmap[i];
-			}
+		if (n) {
+			void* p = nullptr;
+			if (arks_host_alloc(&p, n * 24) != ARKS_OK)
+				die("error: cannot allocate pinned host memory");
+			uint32_t *a = (uint32_t*)p, *b = a + n, *c = b + n;
+			ck(g.h, arks_pmap_export(g.h, a, b, c, n, &n), "arks_pmap_export");
+			pmap.resize(n);
+			for (uint64_t i = 0; i < n; ++i)
+				pmap[i] = PairRow{ a[i], b[i], { c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3] } };
+			arks_host_free(p);
 		}
-		pmap.resize(w);
 	}
+	const double t_export1 = now();
 	// drop imap rows of barcodes that are not keys of indexMultMap (their pairs were never stored)
 	{
 		size_t w = 0;
@@ -1674,8 +1727,10 @@ int main(int argc, char** argv)
 			f << x.first << '\t' << x.second << '\n';
 	}
 	if (params.verbose)
-		printf("wall-clock: start -> _original.gv closed %.3f s (index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s)\n",
-		    t_gv - t_start, t_index1 - t_index0, t_gpu_init, t_map1 - t_map0);
+		printf("wall-clock: start -> _original.gv closed %.3f s (index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s, "
+		       "pair links %.3f s, merge over %d GPUs %.3f s, export %.3f s)\n",
+		    t_gv - t_start, t_index1 - t_index0, t_gpu_init, t_map1 - t_map0, t_links1 - t_links0, params.gpus, t_merge1 - t_links1,
+		    t_export1 - t_merge1);
 	for (auto& gp : gpus) {
 		for (auto& b : gp.batch) {
 			if (!b.bases)

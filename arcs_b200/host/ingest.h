@@ -127,7 +127,26 @@ struct IngestConfig
 	bool mult_known = false; // multiplicities came from -u or a first pass: unknown barcodes are rejected
 	bool verbose = false;
 	int min_mult = 0, max_mult = 0;
+	uint32_t shards = 1; // GPUs the accepted pairs are dealt to, by barcode (barcode_shard)
 };
+
+constexpr uint32_t kMaxShards = 16;
+
+// The GPU a barcode's read pairs go to.  Barcodes are the unit of independence of chromiumRead + pairContigs
+// (every result before the final sum of the pair-link maps is per barcode, Arcs.cpp:1280-1285,1384-1432), so any
+// function of the barcode works; a hash of its text can be evaluated by the parser threads, which do not know
+// the global barcode ids yet.
+inline uint32_t barcode_shard(const char* s, size_t n, uint32_t shards)
+{
+	if (shards <= 1)
+		return 0;
+	uint64_t h = 0xCBF29CE484222325ull; // FNV-1a, then a final mix so that the low bits depend on every byte
+	for (size_t i = 0; i < n; ++i)
+		h = (h ^ (unsigned char)s[i]) * 0x100000001B3ull;
+	h ^= h >> 32;
+	h *= 0x9E3779B97F4A7C15ull;
+	return (uint32_t)((h >> 33) % shards);
+}
 
 // one parsed block of read pairs in caller-provided (pinned) buffers
 struct PairBatch
@@ -136,9 +155,16 @@ struct PairBatch
 	uint32_t* off = nullptr; // 2 n_pairs + 1 offsets into bases
 	uint32_t* bc = nullptr;  // barcode id per pair
 	uint64_t cap_bases = 0;
-	uint32_t cap_pairs = 0;
+	uint32_t cap_pairs = 0; // off holds 2 cap_pairs + 1 + kMaxShards entries
 	uint64_t n_bases = 0;
 	uint32_t n_pairs = 0;
+	// with several shards the pairs are grouped by shard: shard g owns pairs [shard_pair0[g], shard_pair0[g+1]),
+	// its 2 n_g + 1 offsets start at off[2 shard_pair0[g] + g]
+	uint32_t n_shards = 1;
+	uint32_t shard_pair0[kMaxShards + 1] = { 0 };
+	const uint32_t* shard_off(uint32_t g) const { return off + 2 * (size_t)shard_pair0[g] + g; }
+	const uint32_t* shard_bc(uint32_t g) const { return bc + shard_pair0[g]; }
+	uint32_t shard_pairs(uint32_t g) const { return shard_pair0[g + 1] - shard_pair0[g]; }
 };
 
 struct PairSink
@@ -210,11 +236,9 @@ inline void ingest_sequential(SeqReader& rd, Barcodes& bc, const IngestConfig& c
 			ctr.emptybarcode++;
 			continue;
 		}
-		if (!paired || b1 != b2) {
-			// (the reference still looks barcode1 up here, only to count invalid barcodes)
-			continue;
-		}
-		uint32_t id;
+		// the reference looks barcode1 up (and counts an invalid barcode) before it asks whether the
+		// reads pair and the two barcodes agree (Arcs.cpp:1253-1262)
+		uint32_t id = 0;
 		if (cfg.mult_known) {
 			auto it = bc.id.find(b1);
 			if (it == bc.id.end() || !bc.counted[it->second]) {
@@ -222,6 +246,10 @@ inline void ingest_sequential(SeqReader& rd, Barcodes& bc, const IngestConfig& c
 				continue;
 			}
 			id = it->second;
+		}
+		if (!paired || b1 != b2)
+			continue;
+		if (cfg.mult_known) {
 			const int m = bc.mult[id];
 			if (!(m > cfg.min_mult || m < cfg.max_mult)) { // goodmult, Arcs.cpp:1267
 				ctr.skipped_badmult++;
@@ -290,6 +318,12 @@ inline bool parse_block(Block& b, const IngestConfig& cfg, const Barcodes* froze
 		const char *name, *comment, *seq;
 		size_t name_n, comment_n, seq_n;
 	};
+	struct Pending
+	{
+		const char *s0, *s1;
+		uint32_t n0, n1, id, shard;
+	};
+	std::vector<Pending> pending;
 	while (p < end) {
 		Rec r[2];
 		for (int m = 0; m < 2; ++m) {
@@ -350,10 +384,8 @@ inline bool parse_block(Block& b, const IngestConfig& cfg, const Barcodes* froze
 			b.emptybarcode++;
 			continue;
 		}
-		if (!paired || bxn[0] != bxn[1] || memcmp(bx[0], bx[1], bxn[0]) != 0)
-			continue;
-		uint32_t id;
-		if (cfg.mult_known) {
+		uint32_t id = 0;
+		if (cfg.mult_known) { // looked up before the pair / equal-barcode test, as Arcs.cpp:1253-1262 does
 			key.assign(bx[0], bxn[0]);
 			auto it = frozen->id.find(key);
 			if (it == frozen->id.end() || !frozen->counted[it->second]) {
@@ -361,6 +393,10 @@ inline bool parse_block(Block& b, const IngestConfig& cfg, const Barcodes* froze
 				continue;
 			}
 			id = it->second;
+		}
+		if (!paired || bxn[0] != bxn[1] || memcmp(bx[0], bx[1], bxn[0]) != 0)
+			continue;
+		if (cfg.mult_known) {
 			const int mlt = frozen->mult[id];
 			if (!(mlt > cfg.min_mult || mlt < cfg.max_mult)) {
 				b.skipped_badmult++;
@@ -372,6 +408,13 @@ inline bool parse_block(Block& b, const IngestConfig& cfg, const Barcodes* froze
 		PairBatch& o = b.out;
 		if (o.n_pairs >= o.cap_pairs || o.n_bases + r[0].seq_n + r[1].seq_n > o.cap_bases || o.n_bases + r[0].seq_n + r[1].seq_n > 0xFFFFFFF0ull)
 			return false; // cannot happen for blocks cut by the reader; be safe
+		if (cfg.shards > 1) { // laid out by shard once the block is parsed
+			pending.push_back(Pending{ r[0].seq, r[1].seq, (uint32_t)r[0].seq_n, (uint32_t)r[1].seq_n, id,
+			    barcode_shard(bx[0], bxn[0], cfg.shards) });
+			o.n_bases += r[0].seq_n + r[1].seq_n;
+			o.n_pairs++;
+			continue;
+		}
 		o.off[2 * o.n_pairs] = (uint32_t)o.n_bases;
 		memcpy(o.bases + o.n_bases, r[0].seq, r[0].seq_n);
 		o.n_bases += r[0].seq_n;
@@ -381,7 +424,45 @@ inline bool parse_block(Block& b, const IngestConfig& cfg, const Barcodes* froze
 		o.bc[o.n_pairs] = id;
 		o.n_pairs++;
 	}
-	b.out.off[2 * b.out.n_pairs] = (uint32_t)b.out.n_bases;
+	PairBatch& o = b.out;
+	o.n_shards = std::max<uint32_t>(1, cfg.shards);
+	if (cfg.shards > 1) {
+		uint32_t pairs[kMaxShards] = { 0 };
+		uint64_t bases[kMaxShards] = { 0 };
+		for (const Pending& q : pending) {
+			pairs[q.shard]++;
+			bases[q.shard] += q.n0 + q.n1;
+		}
+		uint64_t base_at[kMaxShards];
+		uint32_t pair_at[kMaxShards];
+		uint64_t nb = 0;
+		uint32_t np = 0;
+		for (uint32_t g = 0; g < cfg.shards; ++g) {
+			o.shard_pair0[g] = np;
+			base_at[g] = nb;
+			pair_at[g] = np;
+			np += pairs[g];
+			nb += bases[g];
+		}
+		o.shard_pair0[cfg.shards] = np;
+		for (const Pending& q : pending) {
+			const uint32_t g = q.shard;
+			uint32_t* off = o.off + 2 * (size_t)pair_at[g] + g;
+			off[0] = (uint32_t)base_at[g];
+			memcpy(o.bases + base_at[g], q.s0, q.n0);
+			base_at[g] += q.n0;
+			off[1] = (uint32_t)base_at[g];
+			memcpy(o.bases + base_at[g], q.s1, q.n1);
+			base_at[g] += q.n1;
+			off[2] = (uint32_t)base_at[g];
+			o.bc[pair_at[g]] = q.id;
+			pair_at[g]++;
+		}
+	} else {
+		o.shard_pair0[0] = 0;
+		o.shard_pair0[1] = o.n_pairs;
+		o.off[2 * o.n_pairs] = (uint32_t)o.n_bases;
+	}
 	b.regular = true;
 	return true;
 }

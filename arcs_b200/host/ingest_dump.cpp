@@ -26,6 +26,9 @@ int main(int argc, char** argv)
 	IngestConfig cfg;
 	cfg.min_mult = 50;
 	cfg.max_mult = 10000;
+	// ARKS_SHARDS=G: deal the pairs to G shards by barcode; every P line then ends with its shard
+	if (const char* e = getenv("ARKS_SHARDS"))
+		cfg.shards = (uint32_t)std::max(1, std::min((int)kMaxShards, atoi(e)));
 	if (argc > 5) { // "barcode,count" lines: multiplicities known up front
 		std::ifstream in(argv[5]);
 		std::string line;
@@ -48,14 +51,20 @@ int main(int argc, char** argv)
 		n_pairs++;
 		n_bases += s1.size() + s2.size();
 		if (!bench)
-			lines.push_back("P\t" + bc.name[id] + "\t" + s1 + "\t" + s2);
+			lines.push_back("P\t" + bc.name[id] + "\t" + s1 + "\t" + s2 +
+			                (cfg.shards > 1 ? "\t" + std::to_string(barcode_shard(bc.name[id].data(), bc.name[id].size(), cfg.shards)) : ""));
 	};
 	sink.submit = [&](const PairBatch& b) {
 		n_pairs += b.n_pairs;
 		n_bases += b.n_bases;
-		for (uint32_t i = 0; i < b.n_pairs && !bench; ++i)
-			lines.push_back("P\t" + bc.name[b.bc[i]] + "\t" + std::string(b.bases + b.off[2 * i], b.off[2 * i + 1] - b.off[2 * i]) + "\t" +
-			                std::string(b.bases + b.off[2 * i + 1], b.off[2 * i + 2] - b.off[2 * i + 1]));
+		for (uint32_t g = 0; g < b.n_shards && !bench; ++g) {
+			const uint32_t* off = b.shard_off(g);
+			const uint32_t* ids = b.shard_bc(g);
+			for (uint32_t i = 0; i < b.shard_pairs(g); ++i)
+				lines.push_back("P\t" + bc.name[ids[i]] + "\t" + std::string(b.bases + off[2 * i], off[2 * i + 1] - off[2 * i]) + "\t" +
+				                std::string(b.bases + off[2 * i + 1], off[2 * i + 2] - off[2 * i + 1]) +
+				                (cfg.shards > 1 ? "\t" + std::to_string(g) : ""));
+		}
 	};
 	bool counting = !cfg.mult_known;
 	size_t fast = 0;
@@ -81,7 +90,7 @@ int main(int argc, char** argv)
 			PairBatch pb;
 			mem.emplace_back(opt.block_bytes + 4096);
 			pb.bases = mem.back().data();
-			mem.emplace_back((2ull * cap_pairs + 1) * 4);
+			mem.emplace_back((2ull * cap_pairs + 1 + kMaxShards) * 4);
 			pb.off = (uint32_t*)mem.back().data();
 			mem.emplace_back(cap_pairs * 4ull);
 			pb.bc = (uint32_t*)mem.back().data();

@@ -1,35 +1,39 @@
-"""The one exchange step of the multi-GPU path: read pairs are sharded by barcode, so
-every rank holds the pair-link counters of ITS barcodes only; the link map of the whole run is the
-key-wise sum.  All-gather the ranks' pair keys, form the identical sorted union on every rank, then a
-single all-reduce (sum) over the dense 4 x n_keys counter vector.  Integer sums: the result does not
-depend on the number of ranks or on arrival order.
+"""Multi-GPU plumbing for one process per GPU.
 
-torch.distributed is plumbing here (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Read pairs are sharded by barcode, every rank holds the same k-mer index, so every rank's pair-link map covers
+ITS barcodes only and the link map of the run is the key-wise sum.  The sum itself is `arks_merge_pmap` in the
+C ABI (include/arks_b200.h): NCCL all-gather of the ranks' sorted keys, the same sorted union on every rank, ONE
+ncclAllReduce (sum, uint32) over the dense 4 x n_union counter vector -- all on the device.  What is left here is
+the rendezvous: the NCCL unique id made by rank 0 travels to the other ranks through torch.distributed
+(nccl on the GPU box, gloo in the CPU tests), which is plumbing, not data path.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import api
 
-def merge_pmap(a, b, counts, device):
-    """a, b: uint32 contig indices; counts: uint32 [n,4] of this rank -> (a, b, counts) of all ranks,
-    sorted by (a, b) as integers (the caller re-orders by name rank)."""
-    world = dist.get_world_size()
-    keys = torch.from_numpy((a.astype(np.int64) << 32) | b.astype(np.int64)).to(device)
-    cnt = torch.from_numpy(counts.astype(np.int64)).reshape(-1, 4).to(device)
-    n = torch.tensor([keys.numel()], device=device, dtype=torch.int64)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    mx = max(1, int(max(s.item() for s in sizes)))
-    pad = torch.full((mx,), -1, device=device, dtype=torch.int64)
-    pad[:keys.numel()] = keys
-    gathered = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(gathered, pad)
-    union = torch.unique(torch.cat(gathered))
-    union = union[union >= 0]
-    dense = torch.zeros((union.numel(), 4), device=device, dtype=torch.int64)
-    if keys.numel():
-        dense[torch.searchsorted(union, keys)] = cnt
-    dist.all_reduce(dense, op=dist.ReduceOp.SUM)
-    u = union.cpu().numpy()
-    return (u >> 32).astype(np.uint32), (u & 0xFFFFFFFF).astype(np.uint32), dense.cpu().numpy().astype(np.uint32)
+
+def shard_of_barcode(barcode_id, world):
+    """the rank a barcode's read pairs go to (bench.py; the CLI hashes the barcode text, host/ingest.h)"""
+    return np.asarray(barcode_id) % world
+
+
+def exchange_comm_id(device="cpu", make_id=api.comm_unique_id):
+    """rank 0's communicator id, delivered to every rank of the default process group"""
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if dist.get_rank() == 0:
+        buf = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+    buf = buf.to(device)
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def init_comm(idx, device):
+    """gives `idx` (ArksIndex) its NCCL communicator: rank / size of the default process group"""
+    idx.comm_init_rank(exchange_comm_id(device), dist.get_rank(), dist.get_world_size())
+
+
+def merge_pmap(idx):
+    """collective: afterwards every rank's idx.pmap_rows() / pmap_digest() describe the merged map"""
+    idx.merge_pmap()

@@ -28,6 +28,7 @@ extern "C" {
 #define ARKS_E_OVERFLOW -5  /* a read hit more than ARKS_MAX_TRACK distinct contig ends */
 #define ARKS_E_NOMEM -6
 #define ARKS_E_NONMONOTONE -7 /* head/tail predicate not monotone in max for some sum */
+#define ARKS_E_NCCL -8      /* NCCL could not be loaded or one of its calls failed */
 
 #define ARKS_MIN_K 4   /* ReadsProcessor requires k > 3 (Common/ReadsProcessor.cpp:25) */
 #define ARKS_MAX_K 64  /* 128-bit device keys */
@@ -80,6 +81,12 @@ int arks_host_alloc(void** p, size_t bytes);
  * thread first so that arks_create does not wait for it. */
 int arks_device_init(int device);
 int arks_host_free(void* p);
+/* Multi-GPU hosts: pins the CALLING thread to the cores of the NUMA node the device hangs off
+ * (sysfs topology; a no-op when it cannot be read), so that the pinned buffers the thread
+ * allocates afterwards (first touch) and its copies stay off the inter-socket link.
+ * arks_device_numa_node reports that node (-1: unknown). */
+int arks_bind_thread(int device);
+int arks_device_numa_node(int device, int* node);
 
 /* ---- kernel 1: contig-end k-mer index -------------------------------------------- */
 
@@ -121,6 +128,14 @@ int arks_set_conreci_remap(arks_handle* h, const uint32_t* remap, uint32_t n);
  * checkReadSequence (:366-389) + bestContig (:939-1014) + imap[barcode][end]++. */
 int arks_map_pairs(arks_handle* h, const char* bases, const uint32_t* read_off, const uint32_t* barcode_id,
     uint32_t n_pairs, double j_index, int32_t* conreci_out);
+/* The same call in two halves, for a host that feeds several GPUs from one thread:
+ * arks_map_pairs_begin enqueues the copies and the kernels and returns at once;
+ * arks_map_pairs_end waits until the inputs of every begin since the last end have been
+ * consumed (and, if conreci_out was given, until the results are there).  The input
+ * buffers must not be touched in between.  arks_map_pairs == begin + end. */
+int arks_map_pairs_begin(arks_handle* h, const char* bases, const uint32_t* read_off, const uint32_t* barcode_id,
+    uint32_t n_pairs, double j_index, int32_t* conreci_out);
+int arks_map_pairs_end(arks_handle* h);
 /* Same with device-resident inputs and (optional) device output; fully asynchronous. */
 int arks_map_pairs_device(arks_handle* h, const char* d_bases, const uint32_t* d_read_off,
     const uint32_t* d_barcode_id, uint32_t n_pairs, uint64_t n_bases, double j_index, int32_t* d_conreci_out);
@@ -136,6 +151,8 @@ int arks_map_stats_reset(arks_handle* h);
 int arks_imap_size(arks_handle* h, uint64_t* n_rows);
 int arks_imap_export(arks_handle* h, uint32_t* barcode, uint32_t* contig, uint32_t* head, uint32_t* tail,
     uint64_t cap, uint64_t* n_rows);
+/* Forgets every tally (an empty IndexMap); the index and the map counters stay. */
+int arks_imap_clear(arks_handle* h);
 /* Adds rows to the device imap (used to merge tallies produced elsewhere, e.g. by
  * another GPU that saw part of a barcode, or by ARCS alignment mode). */
 int arks_imap_add(arks_handle* h, const uint32_t* barcode, const uint32_t* contig, const uint32_t* head,
@@ -148,10 +165,39 @@ int arks_imap_add(arks_handle* h, const uint32_t* barcode, const uint32_t* conti
 int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, int min_mult, int max_mult,
     int min_reads, float error_percent, const uint32_t* lexrank, uint32_t n_contigs);
 /* pmap rows (contig a, contig b, counts[4] = HH,HT,TH,TT) with lexrank[a] < lexrank[b],
- * sorted by (lexrank[a], lexrank[b]) = the iteration order of ARCS::PairMap (Arcs.h:115). */
+ * sorted by (lexrank[a], lexrank[b]) = the iteration order of ARCS::PairMap (Arcs.h:115).
+ * The rows are ordered on the device (radix sort); the export is three device->host copies,
+ * at PCIe rate when a / b / counts4 come from arks_host_alloc. */
 int arks_pmap_size(arks_handle* h, uint64_t* n_rows);
 int arks_pmap_export(arks_handle* h, uint32_t* a, uint32_t* b, uint32_t* counts4, uint64_t cap,
     uint64_t* n_rows);
+/* Order-independent 128-bit digest of the map's rows (computed on the device): equal maps
+ * have equal digests whatever the number of GPUs they were accumulated on. */
+int arks_pmap_digest(arks_handle* h, uint64_t digest[2]);
+
+/* ---- multi-GPU: read pairs sharded by barcode, one exchange step ------------------------ */
+
+/* Barcodes are the unit of independence of chromiumRead + pairContigs: with the read pairs
+ * partitioned by barcode over G handles (every handle holding the same index), the
+ * IndexMap shards are disjoint and the PairMap of the run is the key-wise SUM of the
+ * shards' PairMaps.  arks_merge_pmap performs that sum over NCCL: all-gather of the
+ * shards' sorted keys -> the same sorted union everywhere -> ONE ncclAllReduce (sum,
+ * uint32) over the dense 4 x n_union counter vector.  Afterwards every handle's
+ * arks_pmap_size / arks_pmap_export / arks_pmap_digest describe the merged map.
+ * Replaces: nothing upstream (the reference is single-node, Arcs/Arcs.cpp:1378-1435 runs
+ * on one IndexMap); the result equals pairContigs on the union of the shards.
+ *
+ * One process per GPU: rank 0 calls arks_comm_unique_id, the id travels to the other
+ * ranks by any means, every rank calls arks_comm_init_rank with its handle, then -- after
+ * arks_pair_links -- arks_merge_pmap(&h, 1) collectively.
+ * One process, G handles: arks_comm_init_local(handles, G), then
+ * arks_merge_pmap(handles, G) from one thread.  (Handles that share a device -- tests --
+ * exchange with device-to-device copies instead of NCCL.) */
+#define ARKS_COMM_ID_BYTES 128
+int arks_comm_unique_id(uint8_t id[ARKS_COMM_ID_BYTES]);
+int arks_comm_init_rank(arks_handle* h, const uint8_t id[ARKS_COMM_ID_BYTES], int rank, int n_ranks);
+int arks_comm_init_local(arks_handle** handles, int n);
+int arks_merge_pmap(arks_handle** handles, int n_local);
 
 /* The exact head/tail decision table used by arks_pair_links: for sum in [0, n):
  * min_max[sum] = smallest max(head,tail) for which headOrTail() is valid, or

@@ -81,7 +81,7 @@ CASES = sorted(c for c in glob.glob(os.path.join(GOLD, "cli_cases", "*", "expect
 
 
 @pytest.mark.parametrize("argsfile", CASES, ids=[os.path.relpath(c, os.path.join(GOLD, "cli_cases")) for c in CASES])
-@pytest.mark.parametrize("mode", ["one-pass", "two-pass", "2gpu-ids"])
+@pytest.mark.parametrize("mode", ["one-pass", "two-pass", "2gpu-ids", "3gpu-ids"])
 def test_cli_matches_reference_code(argsfile, mode, tmp_path):
     d = os.path.dirname(argsfile)
     tag = os.path.basename(argsfile)[len("expected_"):-len("_args.json")]
@@ -103,15 +103,16 @@ def test_cli_matches_reference_code(argsfile, mode, tmp_path):
     if mode == "two-pass":
         args.append("--two-pass")
     env_gpus = None
-    if mode == "2gpu-ids":
-        # exercises the barcode-sharded multi-handle path; with one physical GPU both shards land on device 0
-        env_gpus = "2"
+    if mode in ("2gpu-ids", "3gpu-ids"):
+        # exercises the barcode-sharded multi-handle path (sharded blocks, one host thread per shard, the merge of
+        # the pair-link maps); with fewer physical GPUs the shards land on device 0
+        env_gpus = mode[0]
     args.append(os.path.join(d, "aln.sam" if arcs_mode else "reads.fq.gz"))
     env = dict(os.environ)
     if env_gpus:
         env["ARKS_GPUS"] = env_gpus
         import torch
-        if torch.cuda.device_count() < 2:  # on a multi-GPU box the shards go to real devices 0 and 1
+        if torch.cuda.device_count() < int(env_gpus):  # on a multi-GPU box the shards go to real devices (NCCL merge)
             env["ARKS_GPUS_SAME_DEVICE"] = "1"
     p = subprocess.run([ARCS] + args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
@@ -160,3 +161,24 @@ def test_cli_several_read_files(how, tmp_path):
     assert read(tmp_path / "o_main.tsv") == read(exp + "_main.tsv")
     assert read(tmp_path / "o_pair.tsv") == read(exp + "_pmap.txt")
     assert read(tmp_path / "bc.tsv") == read(exp + "_bc.tsv")
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_cli_output_is_invariant_in_the_number_of_gpus(n_gpus, tmp_path):
+    """integer sums => `.gv`, `_main.tsv`, the pair map and the barcode counts are byte-identical at
+    1/2/4/8 GPUs.  Real devices, NCCL merge; skipped when the box has fewer."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip("needs %d GPUs" % n_gpus)
+    d = os.path.join(GOLD, "cli_cases", "plain_k60")
+    spec = json.load(open(sorted(glob.glob(os.path.join(d, "expected_*_args.json")))[0]))
+    outs = {}
+    for n in (1, n_gpus):
+        args = ["--arks", "-v", "-f", os.path.join(d, "draft.fa"), "-b", str(tmp_path / ("o%d" % n)), "--barcode-counts",
+                str(tmp_path / ("bc%d.tsv" % n)), "-P", "--gpus", str(n)] + spec["args"] + [os.path.join(d, "reads.fq.gz")]
+        p = subprocess.run([ARCS] + args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        outs[n] = [read(tmp_path / ("o%d%s" % (n, x))) for x in ("_original.gv", "_main.tsv", "_pair.tsv", ".dist.gv")] + [
+            read(tmp_path / ("bc%d.tsv" % n))]
+    assert outs[1] == outs[n_gpus]
+    assert len(outs[1][2].splitlines()) > 0

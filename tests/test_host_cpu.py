@@ -212,6 +212,36 @@ def test_parallel_ingest_equals_sequential_on_strict_fastq(workers, block, gz, t
         assert fast > 0  # the block path did run
 
 
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_blocks_deal_every_barcode_to_one_gpu(shards, tmp_path):
+    """--gpus N: the parser threads lay every block out by shard (barcode_shard of the barcode text); the pairs and
+    their order inside a shard are those of the sequential loop, and a barcode never reaches two shards."""
+    _build_ingest()
+    rng = np.random.default_rng(shards)
+    data = _strict_fastq(rng, 400, barcodes=40, tweak=_tweak_pairing)
+    path = tmp_path / "r.fq"
+    path.write_bytes(data)
+
+    def run(mode, *extra):
+        p = subprocess.run([INGEST, mode, str(path)] + [str(x) for x in extra], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           check=True, env=dict(os.environ, ARKS_SHARDS=str(shards)))
+        return p.stdout.decode().split("\n")
+
+    want = run("seq")
+    got = run("par", 3, 3000)
+    per_shard = lambda lines, g: [l for l in lines if l.startswith("P\t") and l.endswith("\t%d" % g)]  # noqa: E731
+    seen = {}
+    for g in range(shards):
+        assert per_shard(got, g) == per_shard(want, g)
+        for l in per_shard(got, g):
+            assert seen.setdefault(l.split("\t")[1], g) == g
+    assert len(set(seen.values())) > 1
+    assert [l for l in got if not l.startswith("P\t")] == [l for l in want if not l.startswith("P\t")]
+    # one shard: the output carries no shard column and equals the unsharded run
+    plain = subprocess.run([INGEST, "par", str(path), "3", "3000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+    assert sorted(l.rsplit("\t", 1)[0] for l in got if l.startswith("P\t")) == sorted(l for l in plain.split("\n") if l.startswith("P\t"))
+
+
 # base = strict text, c = offset of a record-pair boundary in it
 IRREGULAR = {
     "crlf_in_the_middle": lambda d, c: d[:c] + d[c:].replace(b"\n", b"\r\n", 8),

@@ -20,7 +20,7 @@ if ! skip memcheck; then
 fi
 short_bench() { # label, outfile, env...
   local label=$1 out=$2; shift 2
-  env "$@" timeout 600 python bench.py --pairs ${AB_PAIRS:-6250000} --steps 3 --warmup 3 --no-cpu --no-e2e > $out 2> $out.err
+  env "$@" timeout 600 python bench.py --pairs ${AB_PAIRS:-6250000} --steps 3 --warmup 3 --no-cpu --no-e2e --no-job --invariance-pairs 0 ${AB_CONFIG:+--config $AB_CONFIG} > $out 2> $out.err
   python - "$label" $out <<'PY'
 import json,sys
 try:
@@ -52,12 +52,8 @@ if ! skip full && { [ "$prc" = "0" ] || [ -n "$FORCE_FULL" ]; }; then
 fi
 if ! skip ncu; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O.launches.csv \
-    python bench.py --pairs 3125000 --steps 2 --warmup 3 --no-cpu --no-e2e > $O.launches.log 2>&1
+    python bench.py --pairs 3125000 --steps 2 --warmup 3 --no-cpu --no-e2e --no-job --invariance-pairs 0 ${AB_CONFIG:+--config $AB_CONFIG} > $O.launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:map_ -s 4 -c 2 -o $O.map_full -f \
-    python bench.py --pairs 3125000 --steps 1 --warmup 1 --no-cpu --no-e2e > $O.ncu_full.log 2>&1
+    python bench.py --pairs 3125000 --steps 1 --warmup 1 --no-cpu --no-e2e --no-job --invariance-pairs 0 ${AB_CONFIG:+--config $AB_CONFIG} > $O.ncu_full.log 2>&1
 fi
 ls gpurun_out | tr '\n' ' '
-if [ -n "$WALLCLOCK" ]; then
-  timeout 900 python tools/wallclock.py --genome ${WALL_GENOME:-10000000} --pairs ${WALL_PAIRS:-2000000} > $O.wallclock.json 2> $O.wallclock.err
-  cat $O.wallclock.json
-fi
