@@ -99,6 +99,9 @@ struct arks_handle
 	uint64_t pm_n = 0;
 	uint32_t pm_n_contigs = 0;
 	bool pmap_ready = false;
+	std::vector<uint32_t> ht_table; // headOrTail decision table of the last (min_reads, error_percent)
+	int ht_min_reads = -1;
+	float ht_error = -1.0f;
 	// multi-GPU merge (arks_merge_pmap): NCCL communicator of this handle, or null
 	void* nccl_comm = nullptr;
 	int comm_rank = 0, comm_size = 1;
@@ -213,13 +216,13 @@ bool ht_valid(int mx, int sum, int min_reads, float error_percent)
 }
 
 // min_max[sum] = smallest max in [ceil(sum/2), sum] that passes, UINT32_MAX if none.
-// Verifies monotonicity exhaustively for sum <= 4096 and around the threshold otherwise.
+// Verifies monotonicity exhaustively for sum <= 512 and around the threshold otherwise.
 int build_ht_table(int min_reads, float error_percent, uint32_t n, uint32_t* out)
 {
 	for (uint32_t sum = 0; sum < n; ++sum) {
 		int lo = (int)((sum + 1) / 2), hi = (int)sum;
 		uint32_t thr = UINT32_MAX;
-		if (sum <= 4096) {
+		if (sum <= 512) {
 			for (int m = lo; m <= hi; ++m) {
 				bool v = ht_valid(m, (int)sum, min_reads, error_percent);
 				if (v && thr == UINT32_MAX)
@@ -1254,10 +1257,34 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 	uint32_t maxsum = 0;
 	CU(cudaMemcpyAsync(&maxsum, d_maxsum, 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
-	std::vector<uint32_t> table(maxsum + 1);
-	int rc = build_ht_table(min_reads, error_percent, maxsum + 1, table.data());
-	if (rc)
-		return fail(h, rc, "head/tail predicate is not monotone in max for this (min_reads, error_percent)");
+	// the decision table depends on (min_reads, error_percent) only: kept and extended between calls
+	if (h->ht_min_reads != min_reads || h->ht_error != error_percent) {
+		h->ht_table.clear();
+		h->ht_min_reads = min_reads;
+		h->ht_error = error_percent;
+	}
+	int rc = ARKS_OK;
+	if (h->ht_table.size() < (size_t)maxsum + 1) {
+		const size_t want = std::max<size_t>((size_t)maxsum + 1, 2 * h->ht_table.size());
+		std::vector<uint32_t> t(want);
+		rc = build_ht_table(min_reads, error_percent, (uint32_t)want, t.data());
+		if (rc)
+			return fail(h, rc, "head/tail predicate is not monotone in max for this (min_reads, error_percent)");
+		h->ht_table.swap(t);
+	}
+	const std::vector<uint32_t> table(h->ht_table.begin(), h->ht_table.begin() + maxsum + 1);
+	const bool timing = getenv("ARKS_TIMING") != nullptr;
+	auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_last = tnow();
+	auto lap = [&](const char* what) {
+		if (timing) {
+			cudaStreamSynchronize(st);
+			const double t = tnow();
+			fprintf(stderr, "arks_pair_links: %-34s %.3f ms\n", what, 1e3 * (t - t_last));
+			t_last = t;
+		}
+	};
+	lap("largest sum + decision table");
 	const uint32_t nb = std::max<uint32_t>(n_barcodes, 1);
 	const uint32_t nc = std::max<uint32_t>(n_contigs, 1);
 	const uint32_t n_scan_blocks = (nb + kScanBlock - 1) / kScanBlock;
@@ -1301,9 +1328,11 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 	if ((rc = ensure(h, h->lk_rows, std::max<uint32_t>(n_rows, 1) * 4ull)) || (rc = ensure(h, h->lk_rowbc, std::max<uint32_t>(n_rows, 1) * 4ull)))
 		return rc;
 	uint32_t *d_rows = (uint32_t*)h->lk_rows.p, *d_rowbc = (uint32_t*)h->lk_rowbc.p;
+	lap("count rows per barcode + scan");
 	imap_scatter_kernel<<<g_imap, 256, 0, st>>>(L, d_offs, d_fill, d_rows, d_rowbc);
 	h->launches++;
 	CU(cudaGetLastError());
+	lap("rows grouped by barcode");
 	// 5. the pmap hash.  The number of pair events bounds the number of distinct pairs from above, usually by
 	// far (neighbouring contigs share many barcodes), so the table starts at 2 x min(events, all pairs, 2^25) slots
 	// and is doubled -- and the pass repeated -- if it fills up beyond 70 %.
@@ -1344,6 +1373,10 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 			break;
 		cap <<= 1;
 	}
+	if (timing)
+		fprintf(stderr, "arks_pair_links: %u rows, %llu pair events, %llu distinct pairs, %llu pmap slots\n", n_rows, events, n_pairs,
+		    (unsigned long long)cap);
+	lap("pair kernel into the pmap hash");
 	// 6. order by (rank a, rank b) = std::map<pair<string,string>> iteration order, on the device
 	h->pm_n = n_pairs;
 	const uint64_t n1 = std::max<uint64_t>(n_pairs, 1);
@@ -1367,6 +1400,7 @@ int arks_pair_links(arks_handle* h, const int32_t* mult, uint32_t n_barcodes, in
 	if ((rc = pmap_fill_names(h)))
 		return rc;
 	CU(cudaStreamSynchronize(st));
+	lap("collect + radix sort + gather");
 	h->pmap_ready = true;
 	return ARKS_OK;
 }

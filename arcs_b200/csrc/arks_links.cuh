@@ -202,7 +202,12 @@ __global__ void pmap_gather_counts_kernel(const unsigned long long* __restrict__
     uint32_t* __restrict__ counts)
 {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-		reinterpret_cast<uint4*>(counts)[i] = *reinterpret_cast<const uint4*>(pmap + 4 * (uint64_t)slots[i] + 1);
+	{
+		// the four counters sit at byte 8 of the 32-byte slot: two 8-byte loads (a 16-byte one would be misaligned)
+		const unsigned long long* p = pmap + 4 * (uint64_t)slots[i] + 1;
+		const unsigned long long lo = p[0], hi = p[1];
+		reinterpret_cast<uint4*>(counts)[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+	}
 }
 
 // inv[rank[c]] = smallest contig index with that rank (contigs that share a name share a rank, and their

@@ -122,12 +122,20 @@ struct LaneStats
 	uint32_t kv, ki, found, rec, dups;
 };
 
-// per-read vote state: lane i holds tracked contig end i
+// per-read vote state: lane i holds tracked contig end i.  A read that votes for more than kMaxTrack contig
+// ends (uncut long reads, reads over many short contigs) is counted in several passes over its windows: pass
+// `part` of `parts` (a power of two) only sees the contig ends whose hash falls into it.
 struct Track
 {
 	uint32_t c, cnt, n;
 	bool overflow;
+	uint32_t part, parts;
 };
+
+__device__ __forceinline__ bool track_takes(const Track& t, uint32_t c)
+{
+	return t.parts <= 1u || (((c * 0x9E3779B1u) >> 16) & (t.parts - 1u)) == t.part;
+}
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
@@ -262,6 +270,8 @@ __device__ __forceinline__ bool read_ok(uint32_t n_n, uint32_t n_other, uint32_t
 
 __device__ __forceinline__ void track_add(Track& t, uint32_t lane, uint32_t c, uint32_t cnt)
 {
+	if (!track_takes(t, c)) // warp-uniform: c is
+		return;
 	uint32_t has = __ballot_sync(0xFFFFFFFFu, lane < t.n && t.c == c);
 	if (has) {
 		if (lane == (uint32_t)__ffs(has) - 1)
@@ -587,13 +597,17 @@ struct PairCounters
 
 // argmax over the vote table (ties -> smallest contig end) + Jaccard gate (Arcs.cpp:996-1012).
 // Returns the read's contig end or 0; *passed tells which Jaccard counter to bump.
-__device__ __forceinline__ uint32_t
-warp_decide(const Track& tr, uint32_t total, const MapParams& P, uint32_t lane, bool* passed)
+__device__ __forceinline__ void warp_best(const Track& tr, uint32_t lane, uint32_t& best_cnt, uint32_t& best_c)
 {
 	const uint32_t mycnt = lane < tr.n ? tr.cnt : 0;
-	const uint32_t best_cnt = __reduce_max_sync(0xFFFFFFFFu, mycnt);
+	best_cnt = __reduce_max_sync(0xFFFFFFFFu, mycnt);
 	const uint32_t cand = (best_cnt && lane < tr.n && tr.cnt == best_cnt) ? tr.c : 0xFFFFFFFFu;
-	const uint32_t best_c = __reduce_min_sync(0xFFFFFFFFu, cand);
+	best_c = __reduce_min_sync(0xFFFFFFFFu, cand);
+}
+
+__device__ __forceinline__ uint32_t
+warp_decide(uint32_t best_cnt, uint32_t best_c, uint32_t total, const MapParams& P, bool* passed)
+{
 	bool ok;
 	if (best_cnt == 0)
 		ok = 0.0 > P.j_index;
@@ -713,7 +727,14 @@ warp_process_pair(const WorkRecord& rec, const MapParams& P, WarpRegion* R, uint
 				continue;
 			const uint32_t len = rd ? l2 : l1;
 			const uint32_t total = len >= P.k ? len - P.k + 1 : 0;
-			Track tr{0, 0, 0, false};
+			// votes of the read; repeated in 2, 4, ... passes if it votes for more contig ends than a warp tracks
+			uint32_t best_cnt = 0, best_c = 0xFFFFFFFFu;
+			const LaneStats st0 = st;
+			uint32_t parts = 1;
+#pragma unroll 1
+			for (uint32_t part = 0; part < parts; ++part) {
+			st = st0; // every pass visits every window: the counters of the last pass are the read's
+			Track tr{0, 0, 0, false, part, parts};
 			if (total) {
 				if (shortpair) {
 					Extension E{};
@@ -753,9 +774,26 @@ warp_process_pair(const WorkRecord& rec, const MapParams& P, WarpRegion* R, uint
 					st = lr.st;
 				}
 			}
+			if (tr.overflow) { // warp-uniform
+				if (parts >= 65536u) {
+					pc.overflow = true; // more distinct contig ends than windows: cannot happen
+				} else {
+					parts *= 2;
+					part = 0xFFFFFFFFu; // start over with twice as many passes
+					best_cnt = 0;
+					best_c = 0xFFFFFFFFu;
+					continue;
+				}
+			}
+			uint32_t cnt_p, c_p;
+			warp_best(tr, lane, cnt_p, c_p);
+			if (cnt_p > best_cnt || (cnt_p == best_cnt && cnt_p && c_p < best_c)) {
+				best_cnt = cnt_p;
+				best_c = c_p;
+			}
+			}
 			bool passed;
-			c[rd] = warp_decide(tr, total, P, lane, &passed);
-			pc.overflow |= tr.overflow;
+			c[rd] = warp_decide(best_cnt, best_c, total, P, &passed);
 			if (passed)
 				pc.pass++;
 			else

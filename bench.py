@@ -485,9 +485,9 @@ def main_reference(args, cfg):
     runs = t["t_map_runs"][args.warmup:]
     tot_s = sum(runs)
     v = windows * len(runs) / tot_s
-    sample = ("%d Mbp draft (%d contigs) + %d read pairs of 2x%d bp per step (same generator as the GPU arm's workload%s), -t %d, "
+    sample = ("%.1f Mbp draft (%d contigs) + %d read pairs of 2x%d bp per step (same generator as the GPU arm's workload%s), -t %d, "
               "uncompressed FASTQ from tmpfs, mapping phase (readChroms: kseq parse + BX + bestContig) only, index built once"
-              % (cg["genome"] // 1_000_000, cg["contigs"], n_pairs, L,
+              % (cg["genome"] / 1e6, cg["contigs"], n_pairs, L,
                  "" if cg["genome"] == cfg["genome"] else "; draft bounded to what the CPU indexes in a minute", threads))
     print(json.dumps({
         "impl": "reference", "metric": "read k-mers/s (read->contig lookup)", "value": v, "unit": "k-mers/s",
@@ -770,6 +770,11 @@ def main():
     # the sparse pair-link maps over NCCL (N > 1), and the export of the result to pinned host memory on rank 0
     job = None
     if not args.no_job:
+        idx.imap_clear()
+        step_device()
+        links(mult)  # untimed: the workspaces of the pair-link stage are allocated on first use
+        if world > 1:
+            merge.merge_pmap(idx)
         idx.imap_clear()
         barrier()
         j0, j1, j2, j3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

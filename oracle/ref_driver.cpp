@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <getopt.h>
+#include <iomanip>
 #include <iostream>
 #include <iterator>
 #include <limits>
@@ -130,8 +131,10 @@ createGraphNoBoost(const ARCS::PairMap& pmap, RefGraph& g)
 	}
 }
 
+// removes the vertices of degree > max_degree from g itself, as writePostRemovalGraph does (Arcs.cpp:1593-1610):
+// the ABySS graph is made from what is left
 static void
-writeGraphNoBoost(const std::string& path, RefGraph g, int max_degree)
+writeGraphNoBoost(const std::string& path, RefGraph& g, int max_degree)
 {
 	if (max_degree != 0) {
 		std::vector<int> deg(g.vid.size(), 0);
@@ -167,6 +170,57 @@ writeGraphNoBoost(const std::string& path, RefGraph g, int max_degree)
 			out << ", d=" << e.dist << ", maxd=" << e.maxDist;
 		out << "];\n";
 	}
+	out << "}\n";
+}
+
+// createAbyssGraph + writeAbyssGraph (Arcs.cpp:1615-1672; Graph/DotIO.h:82-114, Graph/ContigGraph.h) without Boost /
+// the ABySS graph classes.  What is pinned by the reference's own code here is the VERTEX ORDER: the walk over the
+// reference's `contigToLength` container (a std::unordered_map<std::string,int> filled by the reference's
+// getContigKmers), two vertices per contig ("name+", "name-").  An edge u -> v also adds its complement v^ -> u^;
+// out-edges are listed per vertex in insertion order.
+static void
+writeAbyssGraphNoBoost(const std::string& path, const ARCS::ContigToLength& contigToLength, const RefGraph& g)
+{
+	std::vector<std::string> vname;
+	std::vector<int> vlen;
+	std::unordered_map<std::string, size_t> vindex;
+	for (const auto& it : contigToLength) {
+		vindex[it.first] = vname.size();
+		vname.push_back(it.first + "+");
+		vlen.push_back(it.second);
+		vname.push_back(it.first + "-");
+		vlen.push_back(it.second);
+	}
+	struct Out
+	{
+		size_t to;
+		int n, d;
+	};
+	std::vector<std::vector<Out>> adj(vname.size());
+	for (const auto& e : g.edges) {
+		const size_t u = vindex[g.vid[e.u]] + (e.orientation < 2 ? 1 : 0);
+		const size_t v = vindex[g.vid[e.v]] + (e.orientation % 2 ? 1 : 0);
+		for (const auto& o : adj[u])
+			if (o.to == v) {
+				std::cerr << "error: Duplicate edge: \"" << vname[u] << "\" -> \"" << vname[v] << '"' << std::endl;
+				exit(EXIT_FAILURE);
+			}
+		int d = (int)params.gap;
+		if (params.dist_est)
+			d = params.dist_mode == ARCS::DIST_MEDIAN ? e.dist : e.maxDist;
+		adj[u].push_back(Out{ v, e.weight, d });
+		const size_t uc = u ^ 1, vc = v ^ 1;
+		if (!(vc == u && uc == v))
+			adj[vc].push_back(Out{ uc, e.weight, d });
+	}
+	std::ofstream out(path.c_str());
+	out << "digraph arcs {\n";
+	for (size_t i = 0; i < vname.size(); ++i)
+		out << '"' << vname[i] << "\" [l=" << vlen[i] << "]\n";
+	for (size_t u = 0; u < vname.size(); ++u)
+		for (const auto& o : adj[u])
+			out << '"' << vname[u] << "\" -> \"" << vname[o.to] << "\" [d=" << o.d << " e=" << std::fixed << std::setprecision(1)
+			    << (float)params.gap << " n=" << o.n << "]\n";
 	out << "}\n";
 }
 
@@ -247,7 +301,7 @@ now()
 int
 main(int argc, char** argv)
 {
-	std::string dump_kmap, dump_trace, dump_imap, dump_pmap, timing_json;
+	std::string dump_kmap, dump_trace, dump_imap, dump_pmap, timing_json, dist_gv;
 	int map_repeats = 1; // --map-repeats N: run the mapping phase N times on one index (timing only when N > 1)
 	static const struct option lo[] = { { "dump-kmap", required_argument, NULL, 1001 },
 		                                { "dump-trace", required_argument, NULL, 1002 },
@@ -263,6 +317,8 @@ main(int argc, char** argv)
 		                                { "arcs", no_argument, NULL, 1011 },
 		                                { "bin_size", required_argument, NULL, 'B' },
 		                                { "map-repeats", required_argument, NULL, 1012 },
+		                                { "dist-gv", required_argument, NULL, 1013 },
+		                                { "gap", required_argument, NULL, 1014 },
 		                                { NULL, 0, NULL, 0 } };
 	params.arks = true;
 	for (int c; (c = getopt_long(argc, argv, "f:c:l:z:b:m:d:e:r:vt:u:j:k:DB:s:", lo, NULL)) != -1;) {
@@ -302,6 +358,8 @@ main(int argc, char** argv)
 		case 'D': params.dist_est = true; break;
 		case 1011: params.arks = false; break;
 		case 1012: map_repeats = std::max(1, atoi(optarg)); break;
+		case 1013: dist_gv = optarg; break;
+		case 1014: arg >> params.gap; break;
 		case 's': arg >> params.seq_id; break;
 		case 'B': arg >> params.dist_bin_size; break;
 		default: return 2;
@@ -370,6 +428,8 @@ main(int argc, char** argv)
 	}
 	writeGraphNoBoost(params.base_name + "_original.gv", g, params.max_degree);
 	double t5 = now();
+	if (!dist_gv.empty())
+		writeAbyssGraphNoBoost(dist_gv, contigToLength, g);
 	if (!params.tsv_name.empty()) {
 		size_t barcodeCount = countBarcodes(imap, indexMultMap);
 		writeTSV(params.tsv_name, imap, pmap, barcodeCount);

@@ -64,6 +64,8 @@ def test_arks_long_demo_cli(tmp_path):
     assert sorted(got) == sorted(want)
     nv = sum(1 for x in want if " -> " not in x and x.startswith('"'))
     assert all(" -> " not in x for x in got[1:1 + nv]) and all(" -> " in x for x in got[1 + nv:-1])
+    # ... and byte for byte what the reference's own code writes on this toolchain (tools/make_dist_gv_fixtures.py)
+    assert read(tmp_path / "long.dist.gv") == read(os.path.join(d, "expected_refcode.dist.gv"))
 
 
 def test_arks_long_demo_stdin(tmp_path):
@@ -120,6 +122,8 @@ def test_cli_matches_reference_code(argsfile, mode, tmp_path):
     assert read(tmp_path / "o_main.tsv") == read(exp + "_main.tsv")
     assert read(tmp_path / "o_pair.tsv") == read(exp + "_pmap.txt")
     assert read(tmp_path / "bc.tsv") == read(exp + "_bc.tsv")
+    # vertex order = the walk over the reference's unordered_map contigToLength (Arcs.cpp:1622), pinned by its own code
+    assert read(tmp_path / "o.dist.gv") == read(exp + "_dist.gv")
     if dist:
         assert read(tmp_path / "dist.tsv") == read(exp + "_dist.tsv")
         assert read(tmp_path / "samples.tsv") == read(exp + "_samples.tsv")

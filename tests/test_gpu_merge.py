@@ -16,14 +16,14 @@ from tools import synth
 pytestmark = pytest.mark.gpu
 
 K, J = 32, 0.4
-LINK_ARGS = (40, 10000, 3, 0.05)  # min_mult, max_mult, min_reads, error_percent
+LINK_ARGS = (40, 10000, 2, 0.05)  # min_mult, max_mult, min_reads, error_percent
 
 
 def _workload():
     rng = np.random.default_rng(77)
     genome, contigs = synth.make_draft(rng, 400000, 5000, K)
     bases, end_off, conreci, names = synth.contig_end_arrays(genome, contigs, K, end_length=2000)
-    rb, roff, bc = synth.make_reads(rng, genome, n_barcodes=240, pairs_per_barcode=50, mol_len=40000, mols_per_barcode=3)
+    rb, roff, bc = synth.make_reads(rng, genome, n_barcodes=240, pairs_per_barcode=120, mol_len=30000, mols_per_barcode=2)
     return bases, end_off, conreci, names, rb, roff, bc
 
 

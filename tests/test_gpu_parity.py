@@ -204,6 +204,48 @@ def test_map_pairs_dense_table(monkeypatch):
                mols_per_barcode=2, sub_rate=0.004, n_rate=0.002, len_jitter=20)
 
 
+@pytest.mark.parametrize("k,piece,n_pieces", [(10, 12, 40), (20, 25, 40), (20, 25, 150), (16, 17, 300)])
+def test_reads_voting_for_more_than_32_contig_ends(k, piece, n_pieces):
+    """bestContig keeps its votes in an unbounded std::map (Arcs.cpp:951-1004); the device tracks 32 contig ends per
+    warp and, for a read that votes for more, counts in 2, 4, ... passes over its windows.  Reads stitched from
+    pieces of many contigs: up to 512 bases (one packed region) and longer (the chunked path), every piece one or
+    two windows long so that many ends tie; the winner gets an extra piece in some reads."""
+    rng = np.random.default_rng(k * 1000 + n_pieces)
+    n_contigs = max(64, n_pieces)
+    contigs = [(str(i + 1), synth.ACGT[rng.integers(0, 4, 700)].tobytes()) for i in range(n_contigs)]
+    ends, names = glue.contig_ends(contigs, 500, 300)
+    bases = np.frombuffer(b"".join(s for s, _ in ends), dtype=np.uint8)
+    end_off = np.zeros(len(ends) + 1, dtype=np.uint64)
+    end_off[1:] = np.cumsum([len(s) for s, _ in ends])
+    conreci = np.array([cr for _, cr in ends], dtype=np.uint32)
+    idx, km = _check_index(k, bases, end_off, conreci)
+    reads = []
+    for r in range(24):
+        order = rng.permutation(len(ends))[:n_pieces]
+        pieces = []
+        for e in order:
+            seq = ends[e][0]
+            a = int(rng.integers(0, len(seq) - piece))
+            pieces.append(seq[a:a + piece])
+        if r % 3 == 0:  # one end gets a second piece: a unique winner
+            seq = ends[order[n_pieces // 2]][0]
+            pieces.append(seq[5:5 + piece])
+        read = b"".join(pieces)
+        mate = synth.revcomp(np.frombuffer(read, dtype=np.uint8)).tobytes() if r % 2 else read
+        reads += [read, mate]
+    rb = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    roff = np.zeros(len(reads) + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(x) for x in reads])
+    bc = np.arange(len(reads) // 2, dtype=np.uint32)
+    for j in (0.0, 0.004, 0.02):
+        idx.map_stats_reset()
+        got = idx.map_pairs(rb, roff, bc, j)
+        want, st = km.map_pairs(rb, roff, j)
+        assert np.array_equal(got, want), (j, got, want)
+        assert idx.map_stats().as_dict() == st.as_dict()
+    assert (want != 0).any() or n_pieces > 100
+
+
 def test_pair_links_match_oracle():
     k, j = 30, 0.4
     rng = np.random.default_rng(11)

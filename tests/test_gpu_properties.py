@@ -23,14 +23,15 @@ def _workload():
 
     import bench
     dev = torch.device("cuda", 0)
-    genome, starts, ends = bench.make_draft_gpu(torch, dev, GENOME, CONTIGS, seed=1)
+    genome, starts, ends = bench.make_draft(torch, dev, GENOME, CONTIGS, seed=1)
     iv = bench.contig_ends(starts, ends)
     end_bases = torch.cat([genome[s:e] for s, e, _ in iv])
     h_end_off = np.zeros(len(iv) + 1, dtype=np.uint64)
     h_end_off[1:] = np.cumsum([e - s for s, e, _ in iv])
     d_end_off = torch.from_numpy(h_end_off.astype(np.int64)).to(dev)
     d_conreci = torch.tensor([c for _, _, c in iv], dtype=torch.int32, device=dev)
-    bases, barcode = bench.make_reads_gpu(torch, dev, genome, PAIRS, PPB, seed=2)
+    cfg = dict(bench.CONFIGS["c2"], ppb=PPB)
+    bases, barcode, _ = bench.make_reads(torch, dev, genome, cfg, PAIRS, seed=2)
     return torch, dev, end_bases, h_end_off, d_end_off, d_conreci, bases, barcode
 
 

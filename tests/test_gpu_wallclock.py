@@ -36,5 +36,5 @@ def test_cli_equals_reference_code_at_bench_scale(name):
                                    barcode.cpu().numpy(), mult, os.cpu_count() or 1)
     assert par["status"] == "ok", par
     assert all(par["identical"].values()) and par["counters_differing"] == []
-    assert par["pair_links"] > 100 and par["gv_edges"] > 0, par  # the comparison is not vacuous
+    assert par["pair_links"] > 50 and par["gv_edges"] > 0, par  # the comparison is not vacuous
     assert cpu["value"] > 0
