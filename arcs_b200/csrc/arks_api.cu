@@ -67,12 +67,6 @@ struct arks_handle
 	unsigned long long* bloom = nullptr;
 	uint64_t bloom_words = 0;
 	int bloom_bits_per_key = 8;
-	// membership filter over the m-mers of the contig text (arks_index.cuh); m = 0: not built
-	unsigned long long* mfilter = nullptr;
-	uint64_t mfilter_words = 0;
-	uint32_t mfilter_m = 0;
-	uint64_t mfilter_mask = 0;
-	int mfilter_enabled = 1;
 	int lane_general = 1;
 	// exact integer thresholds for the Jaccard gate and the N-fraction test
 	uint32_t* d_jmin = nullptr;
@@ -357,10 +351,6 @@ int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const
 	P.use_extension = h->use_extension && h->ct_T.p != nullptr;
 	P.bloom = h->bloom;
 	P.bloom_words = h->bloom_words;
-	P.mfilter = h->mfilter;
-	P.mfilter_words = h->mfilter_words;
-	P.mfilter_m = h->mfilter_m;
-	P.mfilter_mask = h->mfilter_mask;
 	P.lane_general = h->lane_general;
 	if (h->map_mode_pair) {
 		int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_pairs + kMapWarps - 1) / kMapWarps, (uint64_t)h->map_grid));
@@ -630,8 +620,6 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		h->use_extension = atoi(s) ? 0 : 1;
 	if (const char* s = getenv("ARKS_BLOOM_BITS"))
 		h->bloom_bits_per_key = std::max(0, std::min(64, atoi(s)));
-	if (const char* s = getenv("ARKS_MFILTER"))
-		h->mfilter_enabled = atoi(s) ? 1 : 0;
 	if (const char* s = getenv("ARKS_LANE_GENERAL"))
 		h->lane_general = atoi(s) ? 1 : 0;
 	lap("streams, events, limits");
@@ -727,7 +715,7 @@ void arks_destroy(arks_handle* h)
 	comm_release(h);
 	for (void* p : {(void*)h->table, (void*)h->d_ictr, (void*)h->d_mctr, (void*)h->d_remap, (void*)h->imap, (void*)h->d_imap_count,
 	         (void*)h->d_pmap_count, (void*)h->d_scratch, (void*)h->d_jmin, (void*)h->d_nmax, (void*)h->d_work_count,
-	         h->work.p, (void*)h->bloom, (void*)h->mfilter})
+	         h->work.p, (void*)h->bloom})
 		if (p)
 			cudaFree(p);
 	if (h->own_stream)
@@ -946,33 +934,6 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 			h->launches++;
 			CU(cudaGetLastError());
 			CU(cudaStreamSynchronize(h->stream));
-		}
-		// the m-mer filter: m = min(32, k/2 + 1) (2m <= k + 2: two m-mers cover every window around an error);
-		// pointless when nearly every m-mer occurs in a draft of this size (k = 20 on a Gbp draft)
-		if (h->mfilter_enabled && h->bloom_bits_per_key > 0 && c.recorded > 0 && h->g_next && h->ct_T.p && h->use_extension) {
-			const uint32_t m = (uint32_t)std::min(32, (h->k + 2) / 2);
-			const double space = std::pow(4.0, (double)m);
-			if (space >= 64.0 * (double)h->g_next) {
-				uint64_t mm_hi, mm_lo;
-				key_masks((int)m, mm_hi, mm_lo);
-				h->mfilter_m = m;
-				h->mfilter_mask = mm_hi;
-				h->mfilter_words = std::max<uint64_t>(1024, (h->g_next * (uint64_t)h->bloom_bits_per_key + 63) / 64);
-				CU(cudaMalloc(&h->mfilter, h->mfilter_words * 8));
-				CU(cudaMemsetAsync(h->mfilter, 0, h->mfilter_words * 8, h->stream));
-				const int gm = grid_for(h, h->g_next, 256, 16);
-				mfilter_build_kernel<<<gm, 256, 0, h->stream>>>(contig_text(h), m, mm_hi, h->mfilter, h->mfilter_words);
-				const int gp = grid_for(h, (h->g_next + 31) / 32, 256, 16);
-				if (h->kw == 1)
-					mfilter_palindromes_kernel<1><<<gp, 256, 0, h->stream>>>(contig_text(h), (uint32_t)h->k, h->mask_hi, h->mask_lo, m, mm_hi,
-					    h->mfilter, h->mfilter_words);
-				else
-					mfilter_palindromes_kernel<2><<<gp, 256, 0, h->stream>>>(contig_text(h), (uint32_t)h->k, h->mask_hi, h->mask_lo, m, mm_hi,
-					    h->mfilter, h->mfilter_words);
-				h->launches += 2;
-				CU(cudaGetLastError());
-				CU(cudaStreamSynchronize(h->stream));
-			}
 		}
 		h->istats.kmers_valid = c.kmers_valid;
 		h->istats.kmers_null = c.kmers_null;

@@ -381,86 +381,6 @@ __global__ void bloom_build_kernel(const uint8_t* table, uint64_t nslots, unsign
 	}
 }
 
-// ---- sub-k-mer ("m-mer") filter -------------------------------------------------------------------
-// A second membership filter, over the canonical m-mers (m = min(32, k/2 + 1)) of the contig-end text.  It gives
-// the lookup kernel a cheap proof of absence for the windows around a sequencing error: a read window whose k
-// bases contain an m-mer that occurs nowhere in the indexed text cannot be a key of the table (a genuine key is
-// the packing of a text window or of its reverse complement, so all its canonical m-mers are in the filter).
-// The k windows that overlap a substitution at read position t all contain [t-m+1, t] or [t, t+m-1]
-// (2m <= k + 2), so two probes settle them instead of k look-ups.  Two corner cases keep it exact:
-//  * the table also holds the reference's garbage keys of palindromic text windows
-//    (ReadsProcessor.cpp:503-534), which a genuine read window can equal: the m-mers of the k-mer those key bits
-//    spell are inserted too (mfilter_palindromes_kernel);
-//  * a palindromic READ window is looked up under its garbage key, not under its bases: the lookup kernel never
-//    skips a window that may be a palindrome (arks_map.cuh).
-// Positions holding an invalid base are packed as 'A' in the text: they only add a few junk m-mers (a superset
-// is always safe).
-__device__ __forceinline__ uint64_t canonical_mmer(uint64_t f_hi, uint32_t m)
-{
-	const Key128 f{f_hi, 0};
-	const Key128 r = revcomp_key<1>(f, m);
-	return f.hi < r.hi ? f.hi : r.hi;
-}
-
-__device__ __forceinline__ uint64_t mmer_hash(uint64_t canon)
-{
-	return key_hash<1>(Key128{canon, 0}) ^ 0x5851F42D4C957F2Dull; // decorrelated from the k-mer filter when m == k
-}
-
-__device__ __forceinline__ void mfilter_insert(unsigned long long* mf, uint64_t mf_words, uint64_t canon)
-{
-	const BloomProbe b = bloom_probe(mmer_hash(canon), mf_words);
-	atomicOr(mf + b.word, ((unsigned long long)bloom_mask_hi(b.sel) << 32) | bloom_mask_lo(b.sel));
-}
-
-// every m-mer of the packed text (all coordinates in use)
-__global__ void mfilter_build_kernel(ContigText ct, uint32_t m, uint64_t mask_m, unsigned long long* mf, uint64_t mf_words)
-{
-	if (ct.n_bases < m)
-		return;
-	const uint64_t n = ct.n_bases - m + 1;
-	for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n; g += (uint64_t)gridDim.x * blockDim.x) {
-		const Key128 f = extract_window<1>(ct.T + (g >> 4), (uint32_t)(g & 15), mask_m, 0);
-		mfilter_insert(mf, mf_words, canonical_mmer(f.hi, m));
-	}
-}
-
-// bases [o, o + m) of a left-aligned packed k-mer, left-aligned
-__device__ __forceinline__ uint64_t key_sub(const Key128& key, uint32_t o, uint64_t mask_m)
-{
-	uint64_t hi = key.hi, lo = key.lo;
-	if (o >= 32) {
-		hi = lo;
-		lo = 0;
-		o -= 32;
-	}
-	const uint32_t s = 2 * o;
-	return (s ? (hi << s) | (lo >> (64 - s)) : hi) & mask_m;
-}
-
-// the m-mers of the k-mers that the garbage keys of palindromic inserted windows spell
-template <int KW>
-__global__ void mfilter_palindromes_kernel(ContigText ct, uint32_t k, uint64_t mask_hi, uint64_t mask_lo, uint32_t m, uint64_t mask_m,
-    unsigned long long* mf, uint64_t mf_words)
-{
-	const uint64_t n_words = (ct.n_bases + 31) >> 5;
-	for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
-		uint32_t ins = ct.TINS[w];
-		while (ins) {
-			const uint32_t bit = __ffs(ins) - 1;
-			ins &= ins - 1;
-			const uint64_t g = (w << 5) + bit;
-			const Key128 f = extract_window<KW>(ct.T + (g >> 4), (uint32_t)(g & 15), mask_hi, mask_lo);
-			const Key128 r = revcomp_key<KW>(f, k);
-			if (f.hi != r.hi || f.lo != r.lo)
-				continue;
-			const Key128 garbage = palindrome_key(f, (int)k);
-			for (uint32_t o = 0; o + m <= k; ++o)
-				mfilter_insert(mf, mf_words, canonical_mmer(key_sub(garbage, o, mask_m), m));
-		}
-	}
-}
-
 // copies (key, value) of every occupied slot to dense arrays (for tests / dumps)
 template <int KW>
 __global__ void dump_kernel(const uint8_t* table, uint64_t nslots, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* vals,

@@ -98,11 +98,6 @@ struct MapParams
 	const unsigned long long* bloom;
 	uint64_t bloom_words;
 	int lane_general; // 0: the group kernel finishes only reads that equal the contig text (A/B runs)
-	// membership filter over the m-mers of the contig text (arks_index.cuh); null: not built
-	const unsigned long long* mfilter;
-	uint64_t mfilter_words;
-	uint32_t mfilter_m;
-	uint64_t mfilter_mask;
 };
 
 // Everything map_slow_kernel needs to start on a deferred pair, in one aligned 64-byte record (so the
@@ -940,7 +935,6 @@ struct GroupSmem
 		} l;
 	} s;
 	uint32_t PM[32][kGroupMStride]; // per read: invalid base mask, then "window overlaps one", then the lookup mask
-	uint32_t DM[32][kGroupMStride]; // per read: windows (read coordinates) proven absent from the table by the m-mer filter
 	uint32_t woff[33];
 	uint32_t nbad[32];   // per read: N count | other-invalid count << 16
 	uint32_t rinfo[32];  // per read: number of windows | same-strand flag << 16
@@ -1092,113 +1086,6 @@ __device__ __noinline__ ChainResult slot_chain_find(const uint8_t* table, uint64
 __device__ __noinline__ void dilate_row_call(uint32_t* X, uint32_t nmw, uint32_t k)
 {
 	dilate_row(X, nmw, k);
-}
-
-// 32 consecutive bases of a packed stream starting at base a, MSB first
-__device__ __forceinline__ uint64_t bases64(const uint32_t* S, uint32_t a)
-{
-	const uint32_t wi = a >> 4, sh = (a & 15u) * 2u;
-	const uint32_t w0 = S[wi], w1 = S[wi + 1], w2 = S[wi + 2];
-	return ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
-}
-
-// bit i = the window of k bases (k even) starting at read base p0 + i MAY equal its own reverse complement: its
-// innermost `rings` base pairs are complementary (a necessary condition; 4^-rings of random windows pass)
-__device__ __noinline__ uint32_t maybe_palindrome32(const uint32_t* Wr, uint32_t p0, uint32_t k, uint32_t rings)
-{
-	const uint32_t h = k >> 1;
-	uint64_t acc = 0x5555555555555555ull;
-	for (uint32_t r = 0; r < rings; ++r) {
-		const uint64_t z = bases64(Wr, p0 + h - 1 - r) ^ ~bases64(Wr, p0 + h + r);
-		acc &= ~(z | (z >> 1));
-	}
-	// bit 62 - 2i of acc -> bit i
-	uint64_t y = __brevll(acc) >> 1;
-	y = (y | (y >> 1)) & 0x3333333333333333ull;
-	y = (y | (y >> 2)) & 0x0F0F0F0F0F0F0F0Full;
-	y = (y | (y >> 4)) & 0x00FF00FF00FF00FFull;
-	y = (y | (y >> 8)) & 0x0000FFFF0000FFFFull;
-	y = (y | (y >> 16)) & 0x00000000FFFFFFFFull;
-	return (uint32_t)y;
-}
-
-// sets bits [lo, hi) of a mask row
-__device__ __forceinline__ void set_bit_range(uint32_t* row, uint32_t lo, uint32_t hi)
-{
-	for (uint32_t w = lo >> 5; w <= (hi - 1) >> 5; ++w)
-		row[w] |= word_range_mask(lo, hi, w);
-}
-
-// true iff the canonical m-mer starting at read base a is NOT in the m-mer filter
-__device__ __forceinline__ BloomProbe mmer_probe(const uint32_t* Wr, uint32_t a, uint32_t m, uint64_t mask_m, uint64_t mf_words)
-{
-	const uint64_t f = extract_window<1>(Wr, a, mask_m, 0).hi;
-	const Key128 fk{f, 0};
-	const uint64_t r = revcomp_key<1>(fk, m).hi;
-	const uint64_t canon = f < r ? f : r;
-	return bloom_probe(key_hash<1>(Key128{canon, 0}) ^ 0x5851F42D4C957F2Dull, mf_words);
-}
-
-#ifndef ARKS_MM_PROBES
-#define ARKS_MM_PROBES 4
-#endif
-constexpr uint32_t kMaxMismatchProbes = ARKS_MM_PROBES; // mismatching bases per read the m-mer filter is consulted for
-
-// The windows around the mismatching bases of a read (mask Bm, text orientation) that the m-mer filter proves
-// absent from the table, as a mask in READ window coordinates.  Returns false if nothing was proven.
-// (a real call with scalar arguments: the kernel's parameter block must not have its address taken)
-__device__ __noinline__ bool
-mmer_dead_windows(const uint32_t* Wr, const uint32_t* Bm, uint32_t* Dm, uint32_t len, uint32_t total, bool same, uint32_t k, uint32_t m,
-    uint64_t mask_m, const unsigned long long* mf, uint64_t mf_words)
-{
-	const uint32_t nmw = (len + 31) >> 5;
-	for (uint32_t i = 0; i <= nmw; ++i)
-		Dm[i] = 0u;
-	bool any = false;
-	for (uint32_t i = 0; i < nmw; ++i) {
-		uint32_t bits = Bm[i];
-		while (bits) {
-			const uint32_t t = 32u * i + (uint32_t)__ffs(bits) - 1u;
-			bits &= bits - 1u;
-			const uint32_t x = same ? t : len - 1u - t; // the read base
-			// the m-mer that ends at x and the one that starts at x (2m <= k + 2: every window over x holds one of them)
-			const bool a_ok = x + 1u >= m, b_ok = x + m <= len;
-			uint32_t alo = 0, ahi = 0, blo = 0, bhi = 0;
-			BloomProbe pa{0, 0}, pb{0, 0};
-			if (a_ok) {
-				pa = mmer_probe(Wr, x + 1u - m, m, mask_m, mf_words);
-				bloom_load(mf, pa, alo, ahi);
-			}
-			if (b_ok) {
-				pb = mmer_probe(Wr, x, m, mask_m, mf_words);
-				bloom_load(mf, pb, blo, bhi);
-			}
-			if (a_ok && !bloom_test(pa.sel, alo, ahi)) { // windows p with p <= x - m + 1 (and p + k > x)
-				const uint32_t lo = x + 1u > k ? x + 1u - k : 0u;
-				const uint32_t hi = min(x + 2u - m, total);
-				if (hi > lo) {
-					set_bit_range(Dm, lo, hi);
-					any = true;
-				}
-			}
-			if (b_ok && !bloom_test(pb.sel, blo, bhi)) { // windows p with p >= x + m - k (and p <= x)
-				const uint32_t lo = x + m > k ? x + m - k : 0u;
-				const uint32_t hi = min(x + 1u, total);
-				if (hi > lo) {
-					set_bit_range(Dm, lo, hi);
-					any = true;
-				}
-			}
-		}
-	}
-	if (any && (k & 1u) == 0u) {
-		// a palindromic window is looked up under the reference's garbage key, which is not its bases: leave it alone
-		const uint32_t rings = min(3u, k >> 1);
-		for (uint32_t w = 0; w < (total + 31) >> 5; ++w)
-			if (Dm[w])
-				Dm[w] &= ~maybe_palindrome32(Wr, 32u * w, k, rings);
-	}
-	return any;
 }
 
 template <int KW>
@@ -1382,7 +1269,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 						const uint32_t nmw = (len + 31) >> 5;
 						for (uint32_t i = 0; i <= nmw; ++i)
 							Bm[i] = 0u;
-						uint32_t any_mm = 0, n_mm = 0;
+						uint32_t any_mm = 0;
 #pragma unroll kMismatchUnroll
 						for (uint32_t j = 0; j < nw; ++j) {
 							const uint32_t sw = same ? Wr[j] : rev2(~Wr[nw - 1 - j]);
@@ -1393,18 +1280,13 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 							m16 &= (hi_b > lo_b) ? (((1u << hi_b) - 1u) & ~((1u << lo_b) - 1u)) : 0u;
 							reinterpret_cast<uint16_t*>(Bm)[j] = (uint16_t)m16;
 							any_mm |= m16;
-							n_mm += __popc(m16);
 						}
 						const bool any_bad = any_mm != 0 || !clean;
-						bool have_dead = false;
 						if (!any_bad || P.lane_general) {
 							if (any_bad) {
 								if (q0) // stream -> text orientation
 									for (uint32_t i = 0; i < nmw; ++i)
 										Bm[i] = __funnelshift_r(Bm[i], Bm[i + 1], q0);
-								// a few mismatching bases: two m-mer probes each settle the k windows around them
-								if (P.mfilter && any_mm && n_mm <= kMaxMismatchProbes)
-									have_dead = mmer_dead_windows(Wr, Bm, G.DM[lane], len, total, same, P.k, P.mfilter_m, P.mfilter_mask, P.mfilter, P.mfilter_words);
 								if (!clean) {
 									const uint32_t* Ir = G.s.m.INV[lane];
 									for (uint32_t i = 0; i < nmw; ++i) {
@@ -1432,11 +1314,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 								const uint32_t uq = __funnelshift_r(__ldg(P.ct_TUNIQ + w0 + w), __ldg(P.ct_TUNIQ + w0 + w + 1), sh);
 								const uint32_t inside = all_inside ? range : word_range_mask(u_lo, u_hi, w);
 								const uint32_t res = inside & ~badw & ins; // all k bases equal an inserted window of this contig end
-								uint32_t lookup = range & ~invw & ~res;
-								if (have_dead) { // proven absent by the m-mer filter (mask in read window coordinates)
-									const uint32_t* Dm = G.DM[lane];
-									lookup &= ~(same ? Dm[w] : __brev(mask_bits_at(Dm, (int)total - 32 - (int)(32u * w), (int)total)));
-								}
+								const uint32_t lookup = range & ~invw & ~res;
 								r_ki += __popc(invw);
 								r_found += __popc(res);
 								r_rec += __popc(res & uq);

@@ -253,11 +253,11 @@ def _decode_key(key_bytes, k):
 
 
 @pytest.mark.parametrize("k", [20, 30, 32, 40, 60, 64])
-def test_mmer_filter_corner_cases(k):
-    """The lookup kernel skips the windows around a mismatching base when an m-mer they all contain is in no contig
-    end (arks_index.cuh, m-mer filter).  Exactness corners: palindromic read windows (looked up under the
-    reference's garbage key, ReadsProcessor.cpp:503-534), genuine windows that equal the garbage key of a palindromic
-    text window, errors within m bases of the read ends / of each other, and errors inside palindromic tracts."""
+def test_substitutions_around_palindromes_and_garbage_keys(k):
+    """Exactness corners of any shortcut around a mismatching base (seed-and-extend, membership filters): palindromic
+    read windows (looked up under the reference's garbage key, ReadsProcessor.cpp:503-534), genuine windows that equal
+    the garbage key of a palindromic text window, errors at the very ends of a read / next to each other, and errors
+    inside palindromic tracts."""
     rng = np.random.default_rng(900 + k)
     rnd = lambda n: synth.ACGT[rng.integers(0, 4, n)].tobytes()  # noqa: E731
     tracts = [b"AT" * 100, b"CG" * 100, b"ACGT" * 60, b"AATT" * 60, b"GAATTC" * 40]
