@@ -604,7 +604,7 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 	{
 		size_t free_b = 0, total_b = 0;
 		CUC(cudaMemGetInfo(&free_b, &total_b));
-		const double budget = 0.6 * (double)free_b;
+		const double budget = 0.8 * (double)free_b; // the rest: filter, packed text, build scratch, read batches, tallies
 		const double want = (double)max_kmers / load * kSlotBytes;
 		if (want > budget)
 			load = std::min(0.85, (double)max_kmers * kSlotBytes / budget);
@@ -924,7 +924,12 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 		if (c.probe_fail)
 			return fail(h, ARKS_E_CAPACITY, "index table full: more distinct k-mers than max_kmers allows");
 		if (h->bloom_bits_per_key > 0 && c.recorded > 0) {
-			h->bloom_words = std::max<uint64_t>(1024, (c.recorded * (uint64_t)h->bloom_bits_per_key + 63) / 64);
+			// a dense table (huge drafts: load above 0.6) makes every false positive of the filter a long walk over
+			// occupied slots: twice the bits per key then (the filter is far from L2-resident at that size anyway)
+			int bits = h->bloom_bits_per_key;
+			if (!getenv("ARKS_BLOOM_BITS") && (double)c.recorded > 0.6 * (double)h->nslots)
+				bits *= 2;
+			h->bloom_words = std::max<uint64_t>(1024, (c.recorded * (uint64_t)bits + 63) / 64);
 			CU(cudaMalloc(&h->bloom, h->bloom_words * 8));
 			CU(cudaMemsetAsync(h->bloom, 0, h->bloom_words * 8, h->stream));
 			if (h->kw == 1)

@@ -1073,28 +1073,6 @@ __device__ __noinline__ ChainResult slot_chain_find(const uint8_t* table, uint64
 {
 	const Key128 key{key_hi, key_lo};
 	ChainResult r;
-#ifdef ARKS_CHAIN3
-	// the next three slots in one round trip (they share the home slot's 128-byte line three times out of four),
-	// then one at a time
-	{
-		uint64_t s[3], hi[3], lo[3], pi[3];
-		uint32_t val[3];
-#pragma unroll
-		for (int i = 0; i < 3; ++i) {
-			slot = slot + 1 == nslots ? 0 : slot + 1;
-			s[i] = slot;
-			load_slot(table, s[i], hi[i], lo[i], val[i], pi[i]);
-		}
-#pragma unroll
-		for (int i = 0; i < 3; ++i) {
-			r.val = val[i];
-			r.posinfo = pi[i];
-			r.found = slot_matches<KW>(hi[i], lo[i], key);
-			if (r.found || slot_empty<KW>(hi[i], lo[i]))
-				return r;
-		}
-	}
-#endif
 	while (true) {
 		slot = slot + 1 == nslots ? 0 : slot + 1;
 		uint64_t hi, lo;
@@ -1125,18 +1103,6 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 		const uint32_t pair0 = group * kGroupPairs;
 		const uint32_t my_pair = pair0 + (lane >> 1);
 		const bool exists = my_pair < P.n_pairs;
-#ifdef ARKS_PREFETCH_NEXT
-		// the bytes of the group this warp takes next: into L2 while this one is worked on (one 128-byte line per lane
-		// and round; 32 reads of 150 bases are 38 lines)
-		if (group + nwarps < n_groups) {
-			const uint32_t np0 = (group + nwarps) * kGroupPairs;
-			const uint32_t nlast = min(np0 + kGroupPairs, P.n_pairs);
-			const char* a = P.bases + P.read_off[2 * np0];
-			const char* b = P.bases + P.read_off[2 * nlast];
-			for (const char* q = a + 128u * lane; q < b; q += 128u * 32u)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-		}
-#endif
 		// ---- read lane's extent
 		uint32_t off = 0, len = 0;
 		if (exists) {

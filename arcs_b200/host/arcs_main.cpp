@@ -21,6 +21,7 @@
 //  * the alignment mode (no --arks: SAM text in, Arcs.cpp:572-771) tallies read pairs on the host and hands
 //    the IndexMap rows to the same GPU pair-link kernel.
 #include "../../include/arks_b200.h"
+#include "fasta_fast.h"
 #include "ingest.h"
 #include "long_cut.h"
 #include "seq_reader.h"
@@ -39,6 +40,7 @@
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -1096,7 +1098,8 @@ int main(int argc, char** argv)
 	Barcodes bc;
 	Contigs ct;
 	std::vector<Gpu> gpus(params.gpus);
-	double t_index0 = now(), t_index1 = t_index0, t_map0 = t_index0, t_map1 = t_index0, t_gpu_init = 0;
+	double t_index0 = now(), t_index1 = t_index0, t_map0 = t_index0, t_map1 = t_index0, t_gpu_init = 0, t_draft0 = 0, t_draft1 = 0;
+	bool draft_fast = false;
 	if (!params.arks) {
 		// ---- ARCS alignment mode (runArcs :1859-1871): contig sizes from -f (getScaffSizes :549-568) and/or
 		// the SAM headers, tallies from the alignments, then the same pair-link / graph path as ARKS
@@ -1174,42 +1177,96 @@ int main(int argc, char** argv)
 
 	// ---- contigs: getContigKmers (Arcs.cpp:1021-1129) on the GPU
 	std::cout << "\n=>Preprocessing: Gathering draft information..." << stamp() << "\n";
-	std::vector<char> end_bases;
+	std::vector<char> end_bases_vec;
+	std::unique_ptr<char[]> end_bases_raw; // the fast path fills an uninitialised buffer from several threads
+	const char* end_bases_ptr = nullptr;
+	uint64_t end_bases_n = 0;
 	std::vector<uint64_t> end_off(1, 0);
 	std::vector<uint32_t> end_conreci;
+	t_draft0 = now();
 	{
-		SeqReader rd(params.file);
-		if (!rd.ok())
-			die("error: cannot open " + params.file);
-		SeqRecord r;
 		std::unordered_map<std::string, uint32_t> first;
-		while (rd.read(r) >= 0) {
-			ct.total++;
-			r.truncate_at_nul();
-			const int len = (int)r.seq.size();
-			if (len < params.min_size) {
-				ct.skipped++;
-				continue;
-			}
+		// one kept contig: bookkeeping + the extent of its two ends (getContigKmers, Arcs.cpp:1056-1091)
+		auto keep = [&](const std::string& name, int len) -> int {
 			const uint32_t i = (uint32_t)ct.name.size();
-			ct.name.push_back(r.name);
+			ct.name.push_back(name);
 			ct.length.push_back(len);
-			ct.to_length[r.name] = len;
-			auto it = first.find(r.name);
+			ct.to_length[name] = len;
+			auto it = first.find(name);
 			ct.first_of_name.push_back(it == first.end() ? i : it->second);
 			if (it == first.end())
-				first.emplace(r.name, i);
+				first.emplace(name, i);
 			int cut = params.end_length;
 			if (cut == 0 || len <= cut * 2)
 				cut = len / 2;
-			end_bases.insert(end_bases.end(), r.seq.begin(), r.seq.begin() + cut);
-			end_off.push_back(end_bases.size());
+			end_off.push_back(end_off.back() + (uint64_t)cut);
 			end_conreci.push_back(2 * i + 1);
-			end_bases.insert(end_bases.end(), r.seq.end() - cut, r.seq.end());
-			end_off.push_back(end_bases.size());
+			end_off.push_back(end_off.back() + (uint64_t)cut);
 			end_conreci.push_back(2 * i + 2);
+			return cut;
+		};
+		const int threads = (int)std::max(1u, std::thread::hardware_concurrency());
+		arks_host::MappedFasta mf;
+		if (!getenv("ARKS_NO_FAST_FASTA") && mf.open(params.file, threads)) {
+			// plain strict FASTA: every core lists records, then copies the ends (host/fasta_fast.h)
+			draft_fast = true;
+			const auto& recs = mf.records();
+			std::vector<uint32_t> kept;   // record index of every kept contig
+			std::vector<uint32_t> cuts;
+			for (size_t r = 0; r < recs.size(); ++r) {
+				ct.total++;
+				if (recs[r].seq_len > (size_t)INT_MAX)
+					die("error: contig longer than 2^31 bases");
+				const int len = (int)recs[r].seq_len;
+				if (len < params.min_size) {
+					ct.skipped++;
+					continue;
+				}
+				kept.push_back((uint32_t)r);
+				cuts.push_back((uint32_t)keep(std::string(recs[r].name, recs[r].name_n), len));
+			}
+			end_bases_n = end_off.back();
+			end_bases_raw.reset(new char[end_bases_n + 64]);
+			end_bases_ptr = end_bases_raw.get();
+			const size_t nt = std::max<size_t>(1, std::min<size_t>((size_t)threads, kept.size() / 64 + 1));
+			auto work = [&](size_t t) {
+				for (size_t c = kept.size() * t / nt; c < kept.size() * (t + 1) / nt; ++c) {
+					const arks_host::FastaRecord& r = recs[kept[c]];
+					arks_host::MappedFasta::copy_bases(r, 0, cuts[c], end_bases_raw.get() + end_off[2 * c]);
+					arks_host::MappedFasta::copy_bases(r, r.seq_len - cuts[c], cuts[c], end_bases_raw.get() + end_off[2 * c + 1]);
+				}
+			};
+			std::vector<std::thread> th;
+			for (size_t t = 1; t < nt; ++t)
+				th.emplace_back(work, t);
+			work(0);
+			for (auto& x : th)
+				x.join();
+		} else {
+			ct = Contigs();
+			end_off.assign(1, 0);
+			end_conreci.clear();
+			SeqReader rd(params.file);
+			if (!rd.ok())
+				die("error: cannot open " + params.file);
+			SeqRecord r;
+			while (rd.read(r) >= 0) {
+				ct.total++;
+				r.truncate_at_nul();
+				const int len = (int)r.seq.size();
+				if (len < params.min_size) {
+					ct.skipped++;
+					continue;
+				}
+				const int cut = keep(r.name, len);
+				end_bases_vec.insert(end_bases_vec.end(), r.seq.begin(), r.seq.begin() + cut);
+				end_bases_vec.insert(end_bases_vec.end(), r.seq.end() - cut, r.seq.end());
+			}
+			end_bases_ptr = end_bases_vec.data();
+			end_bases_n = end_bases_vec.size();
 		}
 	}
+	t_draft1 = now();
 	if (params.verbose)
 		std::cerr << "Number of contigs:" << ct.name.size() << "\nSize of Contig Array:" << ct.name.size() * 2 + 1 << std::endl;
 
@@ -1235,12 +1292,12 @@ int main(int argc, char** argv)
 			// ARKS_GPUS_SAME_DEVICE=1 (tests): every shard on device 0
 			const int dev = getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d;
 			const double tc0 = now();
-			int rc = arks_create(dev, params.k_value, end_bases.size() + 64, &g.h);
+			int rc = arks_create(dev, params.k_value, end_bases_n + 64, &g.h);
 			t_create[d] = now() - tc0;
 			if (rc != ARKS_OK)
 				die(std::string("error: cannot initialise GPU ") + std::to_string(d) + ": " + arks_last_error(nullptr));
 			if (!end_conreci.empty())
-				ck(g.h, arks_index_add(g.h, end_bases.data(), end_off.data(), end_conreci.data(), (uint32_t)end_conreci.size()),
+				ck(g.h, arks_index_add(g.h, end_bases_ptr, end_off.data(), end_conreci.data(), (uint32_t)end_conreci.size()),
 				    "arks_index_add");
 			ck(g.h, arks_index_finalize(g.h, &ists[d]), "arks_index_finalize");
 			if (any)
@@ -1256,8 +1313,8 @@ int main(int argc, char** argv)
 		t_gpu_init = *std::max_element(t_create.begin(), t_create.end());
 	}
 	t_index1 = now();
-	end_bases.clear();
-	end_bases.shrink_to_fit();
+	std::vector<char>().swap(end_bases_vec);
+	end_bases_raw.reset();
 	if (params.verbose)
 		printf("%s %zu\n%s %zu\n%s %zu\n%s %llu\n%s %llu\n%s %llu\n%s %llu\n%s %llu\n%s %llu\n",
 		    "Total number of contigs in draft genome: ", ct.total, "Total valid contigs: ", ct.name.size(),
@@ -1727,9 +1784,9 @@ int main(int argc, char** argv)
 			f << x.first << '\t' << x.second << '\n';
 	}
 	if (params.verbose)
-		printf("wall-clock: start -> _original.gv closed %.3f s (index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s, "
+		printf("wall-clock: start -> _original.gv closed %.3f s (draft %.3f s%s, index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s, "
 		       "pair links %.3f s, merge over %d GPUs %.3f s, export %.3f s)\n",
-		    t_gv - t_start, t_index1 - t_index0, t_gpu_init, t_map1 - t_map0, t_links1 - t_links0, params.gpus, t_merge1 - t_links1,
+		    t_gv - t_start, t_draft1 - t_draft0, draft_fast ? " on all cores" : " sequential reader", t_index1 - t_index0, t_gpu_init, t_map1 - t_map0, t_links1 - t_links0, params.gpus, t_merge1 - t_links1,
 		    t_export1 - t_merge1);
 	for (auto& gp : gpus) {
 		for (auto& b : gp.batch) {

@@ -726,8 +726,21 @@ class ParallelIngest
 			// the longest prefix made of whole groups of 8 lines: count the newlines, then step back over
 			// the ones that are too many
 			size_t cut = 0;
+			size_t lines_in_block = 0;
 			{
-				const size_t lines = count_newlines(base, have);
+				size_t lines;
+				if (m_map) {
+					// mapped files: the newlines of a fixed grid of chunks are counted by helper threads a window
+					// ahead (one thread cannot scan a file faster than ~8 GB/s); this thread only scans from the
+					// last grid point in front of the block's end
+					const size_t end = m_map_pos + have;
+					count_ahead(end);
+					const size_t g = std::min(end / kGrid, m_grid_cum.size() - 1);
+					lines = (size_t)(m_grid_cum[g] + count_newlines(m_map + g * kGrid, end - g * kGrid) - m_lines_at_pos);
+				} else {
+					lines = count_newlines(base, have);
+				}
+				lines_in_block = lines >= 8 ? lines - (lines & 7u) : 0;
 				size_t drop = lines & 7u; // newlines after the last whole group
 				if (lines >= 8) {
 					const char* last = (const char*)memrchr(base, '\n', have);
@@ -741,6 +754,7 @@ class ParallelIngest
 			}
 			if (m_map) {
 				m_map_pos += cut;
+				m_lines_at_pos += lines_in_block;
 				span = cut ? m_opt.block_bytes : span + m_opt.block_bytes; // no whole pair in sight: look further
 			} else {
 				carry.assign(base + cut, have - cut);
@@ -774,6 +788,36 @@ class ParallelIngest
 		m_cv.notify_all();
 	}
 
+	// newlines in [0, i * kGrid) for every grid point up to (at least) `upto`, counted a window at a time by a few
+	// short-lived threads (which also fault the window's pages in for the parser threads)
+	static constexpr size_t kGrid = 256u << 10;
+	void count_ahead(size_t upto)
+	{
+		upto = std::min(upto, m_map_size);
+		while ((m_grid_cum.size() - 1) * kGrid < upto) {
+			const size_t c0 = m_grid_cum.size() - 1; // first chunk not counted yet
+			const size_t total_chunks = (m_map_size + kGrid - 1) / kGrid;
+			const size_t window_chunks = std::min<size_t>(total_chunks - c0, (128u << 20) / kGrid);
+			const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+			const size_t nt = std::max<size_t>(1, std::min<size_t>({ 8, hw / 2, window_chunks }));
+			std::vector<uint64_t> cnt(window_chunks, 0);
+			auto work = [&](size_t t) {
+				for (size_t c = t; c < window_chunks; c += nt) {
+					const size_t a = (c0 + c) * kGrid, b = std::min(m_map_size, a + kGrid);
+					cnt[c] = count_newlines(m_map + a, b - a);
+				}
+			};
+			std::vector<std::thread> th;
+			for (size_t t = 1; t < nt; ++t)
+				th.emplace_back(work, t);
+			work(0);
+			for (auto& x : th)
+				x.join();
+			for (size_t c = 0; c < window_chunks; ++c)
+				m_grid_cum.push_back(m_grid_cum.back() + cnt[c]);
+		}
+	}
+
 	void worker_loop()
 	{
 		for (;;) {
@@ -802,6 +846,8 @@ class ParallelIngest
 	std::unique_ptr<ByteSource> m_src; // gzip files and pipes
 	const char* m_map = nullptr;
 	size_t m_map_size = 0, m_map_pos = 0; // m_map_pos: first byte that has not been cut into a block (reader thread)
+	std::vector<uint64_t> m_grid_cum = std::vector<uint64_t>(1, 0); // reader thread: see count_ahead
+	uint64_t m_lines_at_pos = 0;                                    // newlines in front of m_map_pos
 	std::vector<std::vector<char>> m_bufs;
 	std::mutex m_mu;
 	std::condition_variable m_cv;

@@ -152,6 +152,60 @@ def test_reader_random_text(tmp_path):
             assert out.split("\n")[:-1] == model_dump(data), data
 
 
+# ---- the draft on all cores (arcs_b200/host/fasta_fast.h) against the faithful reader ----
+def _fast_dump(path, threads):
+    return subprocess.run([DUMP, "--fast", str(path), str(threads)], stdout=subprocess.PIPE, check=True).stdout.decode("latin1").split("\n")[:-1]
+
+
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_fast_fasta_lists_the_records_the_reader_sees(threads, tmp_path):
+    _build()
+    rng = np.random.default_rng(threads)
+    recs = []
+    for i in range(400):
+        L = int(rng.choice([0, 1, 2, 5, 59, 60, 61, 600, 5000, 70000]))
+        seq = "".join("ACGTNacgtnRY>@+"[int(x)] for x in rng.integers(0, 15, L))
+        width = int(rng.choice([0, 60, 61, 7]))
+        if width:  # wrapped: a wrapped line must not start with '>', '@' or '+' (that is the non-strict shape, below)
+            lines = [seq[a:a + width] for a in range(0, L, width)] or [""]
+            lines = [("A" + ln[1:]) if ln[:1] in (">", "@", "+") else ln for ln in lines]
+            seq, body = "".join(lines), "\n".join(lines)
+        else:
+            seq = ("C" + seq[1:]) if seq[:1] in (">", "@", "+") else seq
+            body = seq
+        name = "c%d" % i if i % 7 else ""
+        comment = ["", " len=%d" % L, "\tx y"][i % 3]
+        blank = "\n" if i % 11 == 0 else ""
+        recs.append((name, seq, ">%s%s\n%s\n%s" % (name, comment, body, blank)))
+    text = "".join(r[2] for r in recs)
+    for tail in ("", "no-final-newline"):
+        data = text if not tail else text[:-1] if text.endswith("\n") and not text.endswith("\n\n") else text
+        path = tmp_path / ("d%s.fa" % tail)
+        path.write_bytes(data.encode("latin1"))
+        got = _fast_dump(path, threads)
+        assert got[-1] == "END -1" and len(got) == len(recs) + 1
+        ref = subprocess.run([DUMP, str(path)], stdout=subprocess.PIPE, check=True).stdout.decode("latin1").split("\n")[:-1]
+        for g, r, (name, seq, _) in zip(got, ref, recs):
+            n, gname, gseq, head, tail_b = g.split("\t")
+            rl, rname, _, rseq, _ = r.split("\t")
+            assert (int(n), gname, gseq) == (int(rl), rname, rseq) == (len(seq), name, seq)
+            cut = min(7, len(seq) // 2)
+            assert head == seq[:cut] and tail_b == seq[len(seq) - cut:]
+
+
+@pytest.mark.parametrize("data", [b"@r1\nACGT\n+\nIIII\n", b">a\nAC\r\nGT\n", b">a\nACGT\n+\nIIII\n", b">a\nAC\n@b\nGT\n",
+                                  b">a\nAC\x00GT\n", b"junk\n>a\nACGT\n", b">a\nAC\n>b x\r\nGT\n"])
+def test_fast_fasta_declines_anything_but_strict_plain_fasta(data, tmp_path):
+    _build()
+    path = tmp_path / "d.fa"
+    path.write_bytes(data)
+    assert _fast_dump(path, 2) == ["FALLBACK"]
+    import gzip as _gz
+    with _gz.open(tmp_path / "d.fa.gz", "wb") as f:
+        f.write(b">a\nACGT\n")
+    assert _fast_dump(tmp_path / "d.fa.gz", 2) == ["FALLBACK"]
+
+
 # ---- block-parallel ingest (arcs_b200/host/ingest.h) against the faithful sequential record loop ----
 INGEST = os.path.join(ROOT, "arcs_b200", "bin", "ingest_dump")
 
