@@ -755,7 +755,8 @@ int arks_host_alloc(void** p, size_t bytes)
 	arks_handle* h = nullptr;
 	if (!p)
 		return ARKS_E_ARG;
-	CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+	// portable: pinned for every device of the process (one parsed block feeds several GPUs in `arcs --gpus N`)
+	CU(cudaHostAlloc(p, bytes, cudaHostAllocPortable));
 	return ARKS_OK;
 }
 

@@ -1098,7 +1098,9 @@ int main(int argc, char** argv)
 	Barcodes bc;
 	Contigs ct;
 	std::vector<Gpu> gpus(params.gpus);
-	double t_index0 = now(), t_index1 = t_index0, t_map0 = t_index0, t_map1 = t_index0, t_gpu_init = 0, t_draft0 = 0, t_draft1 = 0;
+	std::thread comm_init; // sets up the NCCL communicator of the pair-link merge while the reads are mapped
+	int comm_rc = ARKS_OK;
+	double t_index0 = now(), t_index1 = t_index0, t_map0 = t_index0, t_map1 = t_index0, t_gpu_init = 0, t_draft0 = 0, t_draft1 = 0, t_ctx0 = t_index0, t_ctx1 = t_index0;
 	bool draft_fast = false;
 	if (!params.arks) {
 		// ---- ARCS alignment mode (runArcs :1859-1871): contig sizes from -f (getScaffSizes :549-568) and/or
@@ -1146,9 +1148,24 @@ int main(int argc, char** argv)
 		t_map1 = now();
 	} else {
 	// the CUDA context is created on a helper thread while the multiplicity file and the draft are parsed
-	std::thread gpu_init([] {
-		for (int d = 0; d < params.gpus; ++d)
-			arks_device_init(getenv("ARKS_GPUS_SAME_DEVICE") ? 0 : d);
+	// (only the GPUs this run uses are made visible: the CUDA runtime initialises every visible device of the node,
+	// which costs seconds on an 8-GPU box)
+	if (!getenv("CUDA_VISIBLE_DEVICES")) {
+		std::string vis;
+		for (int d = 0; d < (getenv("ARKS_GPUS_SAME_DEVICE") ? 1 : params.gpus); ++d)
+			vis += (d ? "," : "") + std::to_string(d);
+		setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+	}
+	t_ctx0 = now();
+	t_ctx1 = t_ctx0;
+	std::thread gpu_init([&t_ctx1] {
+		std::vector<std::thread> th;
+		for (int d = 1; d < params.gpus && !getenv("ARKS_GPUS_SAME_DEVICE"); ++d)
+			th.emplace_back([d] { arks_device_init(d); });
+		arks_device_init(0);
+		for (auto& t : th)
+			t.join();
+		t_ctx1 = now();
 	});
 	// ---- barcode multiplicities
 	const bool have_multfile = !params.multfile.empty();
@@ -1313,6 +1330,14 @@ int main(int argc, char** argv)
 		t_gpu_init = *std::max_element(t_create.begin(), t_create.end());
 	}
 	t_index1 = now();
+	// the NCCL communicator of the merge takes seconds to set up: done on a helper thread while the reads are mapped
+	if (params.gpus > 1)
+		comm_init = std::thread([&] {
+			std::vector<arks_handle*> hs;
+			for (auto& g : gpus)
+				hs.push_back(g.h);
+			comm_rc = arks_comm_init_local(hs.data(), params.gpus);
+		});
 	std::vector<char>().swap(end_bases_vec);
 	end_bases_raw.reset();
 	if (params.verbose)
@@ -1516,7 +1541,9 @@ int main(int argc, char** argv)
 		std::vector<arks_handle*> hs;
 		for (auto& g : gpus)
 			hs.push_back(g.h);
-		ck(hs[0], arks_comm_init_local(hs.data(), params.gpus), "arks_comm_init_local");
+		if (comm_init.joinable())
+			comm_init.join();
+		ck(hs[0], comm_rc, "arks_comm_init_local");
 		ck(hs[0], arks_merge_pmap(hs.data(), params.gpus), "arks_merge_pmap");
 	}
 	const double t_merge1 = now();
@@ -1784,9 +1811,9 @@ int main(int argc, char** argv)
 			f << x.first << '\t' << x.second << '\n';
 	}
 	if (params.verbose)
-		printf("wall-clock: start -> _original.gv closed %.3f s (draft %.3f s%s, index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s, "
+		printf("wall-clock: start -> _original.gv closed %.3f s (CUDA context(s) %.3f s on a helper thread from %.3f s on, draft %.3f s%s, index %.3f s of which CUDA context + table allocation %.3f s, reads %.3f s, "
 		       "pair links %.3f s, merge over %d GPUs %.3f s, export %.3f s)\n",
-		    t_gv - t_start, t_draft1 - t_draft0, draft_fast ? " on all cores" : " sequential reader", t_index1 - t_index0, t_gpu_init, t_map1 - t_map0, t_links1 - t_links0, params.gpus, t_merge1 - t_links1,
+		    t_gv - t_start, t_ctx1 - t_ctx0, t_ctx0 - t_start, t_draft1 - t_draft0, draft_fast ? " on all cores" : " sequential reader", t_index1 - t_index0, t_gpu_init, t_map1 - t_map0, t_links1 - t_links0, params.gpus, t_merge1 - t_links1,
 		    t_export1 - t_merge1);
 	for (auto& gp : gpus) {
 		for (auto& b : gp.batch) {
