@@ -904,13 +904,31 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 	CU(cudaSetDevice(h->device));
 	if (!h->finalized) {
 		int grid = grid_for(h, h->nslots, 256, 16);
+		// the membership filter is sized from the number of k-mers inserted (>= the number of distinct keys, and
+		// within a per cent of it for any real draft), so that it can be filled by the same pass that freezes the table
+		IndexCounters c;
+		CU(cudaMemcpyAsync(&c, h->d_ictr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
+		if (c.probe_fail)
+			return fail(h, ARKS_E_CAPACITY, "index table full: more distinct k-mers than max_kmers allows");
+		if (h->bloom_bits_per_key > 0 && c.kmers_valid > 0) {
+			// a dense table (huge drafts: load above 0.6) makes every false positive of the filter a long walk over
+			// occupied slots: twice the bits per key then (the filter is far from L2-resident at that size anyway)
+			int bits = h->bloom_bits_per_key;
+			if (!getenv("ARKS_BLOOM_BITS") && (double)c.kmers_valid > 0.6 * (double)h->nslots)
+				bits *= 2;
+			h->bloom_words = std::max<uint64_t>(1024, (c.kmers_valid * (uint64_t)bits + 63) / 64);
+			CU(cudaMalloc(&h->bloom, h->bloom_words * 8));
+			CU(cudaMemsetAsync(h->bloom, 0, h->bloom_words * 8, h->stream));
+		}
+		uint32_t* tuniq = (h->g_next && h->ct_T.p) ? (uint32_t*)h->ct_TUNIQ.p : nullptr;
 		if (h->kw == 1)
-			finalize_kernel<1><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr);
+			finalize_kernel<1><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr, h->bloom, h->bloom_words, tuniq);
 		else
-			finalize_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr);
+			finalize_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->d_ictr, h->bloom, h->bloom_words, tuniq);
 		h->launches++;
 		CU(cudaGetLastError());
-		if (h->g_next && h->ct_T.p) {
+		if (tuniq) {
 			int g2 = grid_for(h, (h->g_next + 31) / 32 * 32, 256, 8);
 			if (h->kw == 1)
 				uniq_mask_kernel<1><<<g2, 256, 0, h->stream>>>(contig_text(h), h->table, h->nslots, (uint32_t)h->k, h->mask_hi, h->mask_lo);
@@ -919,28 +937,8 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 			h->launches++;
 			CU(cudaGetLastError());
 		}
-		IndexCounters c;
 		CU(cudaMemcpyAsync(&c, h->d_ictr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
 		CU(cudaStreamSynchronize(h->stream));
-		if (c.probe_fail)
-			return fail(h, ARKS_E_CAPACITY, "index table full: more distinct k-mers than max_kmers allows");
-		if (h->bloom_bits_per_key > 0 && c.recorded > 0) {
-			// a dense table (huge drafts: load above 0.6) makes every false positive of the filter a long walk over
-			// occupied slots: twice the bits per key then (the filter is far from L2-resident at that size anyway)
-			int bits = h->bloom_bits_per_key;
-			if (!getenv("ARKS_BLOOM_BITS") && (double)c.recorded > 0.6 * (double)h->nslots)
-				bits *= 2;
-			h->bloom_words = std::max<uint64_t>(1024, (c.recorded * (uint64_t)bits + 63) / 64);
-			CU(cudaMalloc(&h->bloom, h->bloom_words * 8));
-			CU(cudaMemsetAsync(h->bloom, 0, h->bloom_words * 8, h->stream));
-			if (h->kw == 1)
-				bloom_build_kernel<1><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->bloom, h->bloom_words);
-			else
-				bloom_build_kernel<2><<<grid, 256, 0, h->stream>>>(h->table, h->nslots, h->bloom, h->bloom_words);
-			h->launches++;
-			CU(cudaGetLastError());
-			CU(cudaStreamSynchronize(h->stream));
-		}
 		h->istats.kmers_valid = c.kmers_valid;
 		h->istats.kmers_null = c.kmers_null;
 		h->istats.recorded = c.recorded;

@@ -124,7 +124,9 @@ cas128(uint64_t* p, uint64_t c_lo, uint64_t c_hi, uint64_t n_lo, uint64_t n_hi, 
 }
 
 // Finds or claims the slot of `key`; returns the slot's base address (nullptr if the table
-// is full) and whether this call claimed it.
+// is full) and whether this call claimed it.  The compare-and-swap against the empty pattern IS the probe: it
+// returns what the slot holds, so no load goes in front of it (one memory round trip less per k-mer, and most
+// k-mers of a draft are first occurrences).
 template <int KW>
 __device__ __forceinline__ uint64_t* find_or_claim(uint8_t* table, uint64_t nslots, const Key128& key, bool* claimed)
 {
@@ -134,26 +136,20 @@ __device__ __forceinline__ uint64_t* find_or_claim(uint8_t* table, uint64_t nslo
 		uint64_t* p = reinterpret_cast<uint64_t*>(table + slot * kSlotBytes);
 		if (KW == 1) {
 			unsigned long long* pk = reinterpret_cast<unsigned long long*>(p);
-			unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(pk);
+			const unsigned long long cur = atomicCAS(pk, (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
 			if (cur == kEmptyKey) {
-				cur = atomicCAS(pk, (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
-				if (cur == kEmptyKey) {
-					*claimed = true;
-					return p;
-				}
+				*claimed = true;
+				return p;
 			}
 			if (cur == key.hi)
 				return p;
 		} else {
 			uint64_t hi, lo;
-			asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(hi), "=l"(lo) : "l"(p));
+			// memory order of the pair is (p[0], p[1]) = (hi, lo); b128 = {low 64, high 64}
+			cas128(p, kEmptyKey, kEmptyKey, key.hi, key.lo, hi, lo);
 			if (hi == kEmptyKey && lo == kEmptyKey) {
-				// memory order of the pair is (p[0], p[1]) = (hi, lo); b128 = {low 64, high 64}
-				cas128(p, kEmptyKey, kEmptyKey, key.hi, key.lo, hi, lo);
-				if (hi == kEmptyKey && lo == kEmptyKey) {
-					*claimed = true;
-					return p;
-				}
+				*claimed = true;
+				return p;
 			}
 			if (hi == key.hi && lo == key.lo)
 				return p;
@@ -163,9 +159,12 @@ __device__ __forceinline__ uint64_t* find_or_claim(uint8_t* table, uint64_t nslo
 	return nullptr;
 }
 
-__device__ __forceinline__ void note_occurrence(unsigned long long* wp, uint32_t conreci)
+// `guess`: what the bookkeeping word probably holds (kEmptyW right after a claim); a wrong guess costs one failed
+// compare-and-swap, which returns the real value
+__device__ __forceinline__ void note_occurrence(unsigned long long* wp, uint32_t conreci, unsigned long long guess)
 {
-	unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(wp);
+	unsigned long long old = guess;
+	bool seen = false; // `old` was read from memory (by a failed compare-and-swap)
 	while (true) {
 		unsigned long long nw;
 		if (old == kEmptyW) {
@@ -179,12 +178,13 @@ __device__ __forceinline__ void note_occurrence(unsigned long long* wp, uint32_t
 			else
 				nw = old | kMultiFlag;
 		}
-		if (nw == old)
+		if (nw == old && seen)
 			return;
 		unsigned long long prev = atomicCAS(wp, old, nw);
 		if (prev == old)
 			return;
 		old = prev;
+		seen = true;
 	}
 }
 
@@ -266,7 +266,10 @@ insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char*
 					} else {
 						if (claimed)
 							sp[3] = end_tag | ((uint64_t)fwd_canon << kPosBits) | (g0 + p);
-						note_occurrence(reinterpret_cast<unsigned long long*>(sp + 2), cr);
+						// a claimed slot's word is still unset (unless another occurrence of the key got in between); for a
+						// key that was there already the likeliest content is "seen once in this very contig end"
+						note_occurrence(reinterpret_cast<unsigned long long*>(sp + 2), cr,
+						    claimed ? (unsigned long long)kEmptyW : (((unsigned long long)cr << 32) | 1ull));
 						my_valid++;
 						inserted = true;
 					}
@@ -287,17 +290,22 @@ insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char*
 }
 
 // ---- finalize ------------------------------------------------------------------------
-// Slots touched since the last finalize carry a bookkeeping word with a non-zero high
-// half (conreci >= 1); finalized slots carry (0 << 32) | value.  Re-finalising is a no-op.
+// One pass over the table: collapses the build bookkeeping of every key into its final value (+ the counters),
+// adds the key to the membership filter (bloom_probe in arks_device.cuh; keys whose value is 0 are included: a
+// lookup that finds them counts as "found", Arcs.cpp:969-971), and marks the text window that claimed the slot
+// as "unique" when the key maps to one contig end (the other occurrences of such a key -- rare -- are settled by
+// uniq_mask_kernel).  Slots already finalised (high half of the word 0) are left alone.
 template <int KW>
-__global__ void finalize_kernel(uint8_t* table, uint64_t nslots, IndexCounters* ctr)
+__global__ void finalize_kernel(uint8_t* table, uint64_t nslots, IndexCounters* ctr, unsigned long long* bloom, uint64_t bloom_words,
+    uint32_t* TUNIQ)
 {
 	unsigned long long rec = 0, uniq = 0, cmin = 0;
 	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t* p = reinterpret_cast<uint64_t*>(table + sidx * kSlotBytes);
-		if (slot_empty<KW>(p[0], p[1]))
+		const ulonglong4 sl = *reinterpret_cast<const ulonglong4*>(p);
+		if (slot_empty<KW>(sl.x, sl.y))
 			continue;
-		uint64_t w = p[2];
+		const uint64_t w = sl.z;
 		if ((w >> 32) == 0)
 			continue; // already final
 		uint32_t mc = (uint32_t)(w >> 32);
@@ -306,6 +314,15 @@ __global__ void finalize_kernel(uint8_t* table, uint64_t nslots, IndexCounters* 
 		rec++;
 		uniq += multi ? 0 : 1;
 		cmin += (uint32_t)w & 0x7FFFFFFFu;
+		if (bloom) {
+			const Key128 key{sl.x, KW == 2 ? sl.y : 0ull};
+			const BloomProbe b = bloom_probe(key_hash<KW>(key), bloom_words);
+			atomicOr(bloom + b.word, ((unsigned long long)bloom_mask_hi(b.sel) << 32) | bloom_mask_lo(b.sel));
+		}
+		if (!multi && TUNIQ) {
+			const uint64_t g = sl.w & kPosMask;
+			atomicOr(TUNIQ + (g >> 5), 1u << (g & 31u));
+		}
 	}
 	// block reduce through warp sums
 	for (int o = 16; o > 0; o >>= 1) {
@@ -349,7 +366,11 @@ __global__ void uniq_mask_kernel(ContigText ct, const uint8_t* table, uint64_t n
 	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	const uint32_t lane = threadIdx.x & 31;
 	for (uint64_t w = warp0; w < n_words; w += nwarps) {
-		const uint32_t ins = ct.TINS[w];
+		// windows already marked by finalize_kernel (the occurrence that claimed its key's slot) need no lookup
+		const uint32_t have = ct.TUNIQ[w];
+		const uint32_t ins = ct.TINS[w] & ~have;
+		if (ins == 0u)
+			continue;
 		bool uq = false;
 		if ((ins >> lane) & 1u) {
 			const uint64_t g = (w << 5) + lane;
@@ -360,24 +381,8 @@ __global__ void uniq_mask_kernel(ContigText ct, const uint8_t* table, uint64_t n
 			uq = v != 0 && v != kMiss;
 		}
 		const uint32_t word = __ballot_sync(0xFFFFFFFFu, uq);
-		if (lane == 0)
-			ct.TUNIQ[w] = word;
-	}
-}
-
-// membership prefilter over every key of the frozen table (bloom_probe in arks_device.cuh); keys whose
-// value is 0 are included: a lookup that finds them counts as "found" (Arcs.cpp:969-971)
-template <int KW>
-__global__ void bloom_build_kernel(const uint8_t* table, uint64_t nslots, unsigned long long* bloom, uint64_t n_words)
-{
-	for (uint64_t sidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; sidx < nslots; sidx += (uint64_t)gridDim.x * blockDim.x) {
-		const uint64_t* p = reinterpret_cast<const uint64_t*>(table + sidx * kSlotBytes);
-		const uint64_t hi = p[0], lo = p[1];
-		if (slot_empty<KW>(hi, lo))
-			continue;
-		const Key128 key{hi, KW == 2 ? lo : 0ull};
-		const BloomProbe b = bloom_probe(key_hash<KW>(key), n_words);
-		atomicOr(bloom + b.word, ((unsigned long long)bloom_mask_hi(b.sel) << 32) | bloom_mask_lo(b.sel));
+		if (lane == 0 && word)
+			ct.TUNIQ[w] = have | word;
 	}
 }
 

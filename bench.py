@@ -647,15 +647,26 @@ def main():
             sel = torch.nonzero(barcode < nb).flatten()
             return (bases.view(-1, 2 * RL)[sel].reshape(-1, RL).cpu().numpy(), barcode[sel].cpu().numpy())
 
-        s_reads, s_bc = sample(args.parity_pairs)
-        parity, cpu = parity_sample(np, cfg, genome_np, starts, ends, s_reads, s_bc, mult, threads)
+        if cfg["genome"] <= max(cfg["cpu_genome"], 200_000_000):
+            s_reads, s_bc = sample(args.parity_pairs)
+            parity, cpu = parity_sample(np, cfg, genome_np, starts, ends, s_reads, s_bc, mult, threads)
+        else:
+            # the CPU indexes ~1.6 M draft k-mers per second: a Gbp draft would take minutes.  Same generators, same
+            # parameters, draft bounded to cfg.cpu_genome (as in the reference arm)
+            pg = dict(cfg, genome=cfg["cpu_genome"], contigs=max(2, cfg["contigs"] * cfg["cpu_genome"] // cfg["genome"]))
+            p_genome, p_starts, p_ends = make_draft(torch, dev, pg["genome"], pg["contigs"], seed=1)
+            p_bases, p_bc, p_mult = make_reads(torch, dev, p_genome, pg, args.parity_pairs, seed=2)
+            parity, cpu = parity_sample(np, pg, p_genome.cpu().numpy(), p_starts, p_ends, p_bases.view(-1, RL).cpu().numpy(),
+                                        p_bc.cpu().numpy(), p_mult, threads)
+            parity["note"] += "; draft bounded to %d Mbp for the CPU side (same generators and parameters)" % (pg["genome"] // 1_000_000)
+            del p_genome, p_bases, p_bc
         if parity.get("status") not in ("ok", "oracle/_ref/arcs_ref not built"):
             print(json.dumps({"parity_sample": parity}), file=sys.stderr)
             raise SystemExit("bench.py: parity sample failed: the CUDA path and the reference's code disagree")
         if not args.no_cli:
             s_reads, s_bc = sample(args.cli_pairs)
             cliw = cli_wall(np, cfg, genome_np, starts, ends, s_reads, s_bc, mult)
-        del genome_np, s_reads, s_bc
+        del genome_np
 
     # one counted pass to learn the work per step
     idx.map_stats_reset()
