@@ -1380,9 +1380,17 @@ int main(int argc, char** argv)
 		};
 		// block-parallel parsing (ingest.h) unless -D needs the pairs' input order or ARKS_PARSE_THREADS=0
 		arks_host::ParallelIngestOptions popt;
-		popt.workers = (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency()));
+		{
+			// parser threads: the cores of the host minus the reader, the committer, the driver's threads; 4 at least
+			// (the blocks they work on are in flight anyway), 24 at most (memory bandwidth, not cores, bounds it by then)
+			const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+			popt.workers = (int)std::min(24u, std::max(4u, hw > 4 ? hw - 4 : 1u));
+		}
 		if (const char* e = getenv("ARKS_PARSE_THREADS"))
 			popt.workers = atoi(e);
+		// several GPUs: every block is dealt to all of them, so the blocks grow with their number (the per-GPU part
+		// of a block stays about 4 MB and the committing thread issues as many calls per byte as with one GPU)
+		popt.block_bytes *= (size_t)std::min(params.gpus, 8);
 		if (const char* e = getenv("ARKS_PARSE_BLOCK_MB"))
 			popt.block_bytes = (size_t)std::max(1, atoi(e)) << 20;
 		const bool parallel = popt.workers > 0 && !params.dist_est;
