@@ -28,6 +28,11 @@ namespace arks {
 
 constexpr int kTileWindows = 1024;
 constexpr int kInsertThreads = 256;
+constexpr int kInsertBatch = kTileWindows / kInsertThreads; // windows per thread and tile
+#ifndef ARKS_INSERT_MIN_BLOCKS
+#define ARKS_INSERT_MIN_BLOCKS 3
+#endif
+constexpr int kInsertMinBlocks = ARKS_INSERT_MIN_BLOCKS; // CTAs per SM the register budget is sized for
 // words of packed region per tile: (1024 + 64 - 1 + 15)/16 = 68, +5 slack for extraction
 constexpr int kTileWords = 68 + 6;
 constexpr int kTileInvWords = 35 + 3;
@@ -123,69 +128,57 @@ cas128(uint64_t* p, uint64_t c_lo, uint64_t c_hi, uint64_t n_lo, uint64_t n_hi, 
 	             : "memory");
 }
 
-// Finds or claims the slot of `key`; returns the slot's base address (nullptr if the table
-// is full) and whether this call claimed it.  The compare-and-swap against the empty pattern IS the probe: it
-// returns what the slot holds, so no load goes in front of it (one memory round trip less per k-mer, and most
-// k-mers of a draft are first occurrences).
-template <int KW>
-__device__ __forceinline__ uint64_t* find_or_claim(uint8_t* table, uint64_t nslots, const Key128& key, bool* claimed)
+// the bookkeeping word after one more occurrence of its key in contig end `conreci`
+__device__ __forceinline__ unsigned long long note_next(unsigned long long old, uint32_t conreci)
 {
-	uint64_t slot = hash_to_slot(key_hash<KW>(key), nslots);
-	*claimed = false;
-	for (uint64_t probes = 0; probes < nslots; ++probes) {
-		uint64_t* p = reinterpret_cast<uint64_t*>(table + slot * kSlotBytes);
-		if (KW == 1) {
-			unsigned long long* pk = reinterpret_cast<unsigned long long*>(p);
-			const unsigned long long cur = atomicCAS(pk, (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
-			if (cur == kEmptyKey) {
-				*claimed = true;
-				return p;
-			}
-			if (cur == key.hi)
-				return p;
-		} else {
-			uint64_t hi, lo;
-			// memory order of the pair is (p[0], p[1]) = (hi, lo); b128 = {low 64, high 64}
-			cas128(p, kEmptyKey, kEmptyKey, key.hi, key.lo, hi, lo);
-			if (hi == kEmptyKey && lo == kEmptyKey) {
-				*claimed = true;
-				return p;
-			}
-			if (hi == key.hi && lo == key.lo)
-				return p;
-		}
-		slot = slot + 1 == nslots ? 0 : slot + 1;
-	}
-	return nullptr;
+	if (old == kEmptyW)
+		return ((unsigned long long)conreci << 32) | 1ull;
+	const uint32_t mc = (uint32_t)(old >> 32);
+	if (conreci < mc)
+		return ((unsigned long long)conreci << 32) | kMultiFlag | 1ull;
+	if (conreci == mc)
+		return old + 1ull;
+	return old | kMultiFlag;
 }
 
-// `guess`: what the bookkeeping word probably holds (kEmptyW right after a claim); a wrong guess costs one failed
-// compare-and-swap, which returns the real value
-__device__ __forceinline__ void note_occurrence(unsigned long long* wp, uint32_t conreci, unsigned long long guess)
+// `old` was read from memory (by a failed compare-and-swap): retry until the occurrence is in
+__device__ __forceinline__ void note_occurrence_from(unsigned long long* wp, uint32_t conreci, unsigned long long old)
 {
-	unsigned long long old = guess;
-	bool seen = false; // `old` was read from memory (by a failed compare-and-swap)
 	while (true) {
-		unsigned long long nw;
-		if (old == kEmptyW) {
-			nw = ((unsigned long long)conreci << 32) | 1ull;
-		} else {
-			uint32_t mc = (uint32_t)(old >> 32);
-			if (conreci < mc)
-				nw = ((unsigned long long)conreci << 32) | kMultiFlag | 1ull;
-			else if (conreci == mc)
-				nw = old + 1ull;
-			else
-				nw = old | kMultiFlag;
-		}
-		if (nw == old && seen)
+		const unsigned long long nw = note_next(old, conreci);
+		if (nw == old)
 			return;
-		unsigned long long prev = atomicCAS(wp, old, nw);
+		const unsigned long long prev = atomicCAS(wp, old, nw);
 		if (prev == old)
 			return;
 		old = prev;
-		seen = true;
 	}
+}
+
+// continues the probe sequence behind `slot` (whose first compare-and-swap met another key)
+template <int KW>
+__device__ __noinline__ uint64_t* find_or_claim_behind(uint8_t* table, uint64_t nslots, uint64_t slot, uint64_t key_hi, uint64_t key_lo, bool* claimed)
+{
+	const Key128 key{key_hi, key_lo};
+	*claimed = false;
+	for (uint64_t probes = 1; probes < nslots; ++probes) {
+		slot = slot + 1 == nslots ? 0 : slot + 1;
+		uint64_t* p = reinterpret_cast<uint64_t*>(table + slot * kSlotBytes);
+		uint64_t hi, lo;
+		if (KW == 1) {
+			hi = atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)kEmptyKey, (unsigned long long)key.hi);
+			lo = hi == kEmptyKey ? kEmptyKey : key.lo;
+		} else {
+			cas128(p, kEmptyKey, kEmptyKey, key.hi, key.lo, hi, lo);
+		}
+		if (hi == kEmptyKey && lo == kEmptyKey) {
+			*claimed = true;
+			return p;
+		}
+		if (hi == key.hi && lo == key.lo)
+			return p;
+	}
+	return nullptr;
 }
 
 struct IndexTile
@@ -209,7 +202,7 @@ struct ContigText
 };
 
 template <int KW>
-__global__ void __launch_bounds__(kInsertThreads)
+__global__ void __launch_bounds__(kInsertThreads, kInsertMinBlocks)
 insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char* __restrict__ bases,
     const uint64_t* __restrict__ end_off, const uint32_t* __restrict__ conreci, const uint32_t* __restrict__ skip,
     const uint64_t* __restrict__ batch_g0, uint32_t first_global_end, ContigText ct, uint8_t* table, uint64_t nslots, uint32_t k,
@@ -250,33 +243,76 @@ insert_kernel(const IndexTile* __restrict__ tiles, uint32_t n_tiles, const char*
 		const uint32_t cr = conreci[tl.end];
 		const uint64_t gpos0 = s + tl.start;
 		const uint64_t end_tag = (uint64_t)(first_global_end + tl.end) << 40;
-		for (uint32_t pb = 0; pb < nw; pb += blockDim.x) { // warp-uniform trip count
-			const uint32_t p = pb + threadIdx.x;
-			bool inserted = false;
+		// Every thread takes kInsertBatch windows of the tile and walks them through the insert in STAGES, so that its
+		// memory round trips overlap instead of forming one dependent chain per window (the kernel was latency-bound:
+		// issue-active 14 %, DRAM 16 %): all keys -> all first compare-and-swaps (the probe IS the claim: it returns
+		// what the slot holds) -> all bookkeeping compare-and-swaps (guessing the word: unset after a claim, "seen once
+		// in this contig end" otherwise) -> the few that need another round.
+		Key128 key[kInsertBatch];
+		uint64_t slot[kInsertBatch], ohi[kInsertBatch], olo[kInsertBatch];
+		uint32_t act = 0, fcm = 0;
+#pragma unroll
+		for (int r = 0; r < kInsertBatch; ++r) {
+			const uint32_t p = r * kInsertThreads + threadIdx.x;
+			key[r] = Key128{0, 0};
+			slot[r] = 0;
 			if (p < nw) {
 				const uint64_t gp = gpos0 + p;
 				const bool skipped = (skip[gp >> 5] >> (gp & 31)) & 1u;
 				if (!skipped && !window_invalid(INV, p, k)) {
 					bool fwd_canon;
-					Key128 key = canonical_key<KW>(W, RC, p, k, nwords * 16, mask_hi, mask_lo, &fwd_canon);
-					bool claimed;
-					uint64_t* sp = find_or_claim<KW>(table, nslots, key, &claimed);
-					if (sp == nullptr) {
-						fail = true;
-					} else {
-						if (claimed)
-							sp[3] = end_tag | ((uint64_t)fwd_canon << kPosBits) | (g0 + p);
-						// a claimed slot's word is still unset (unless another occurrence of the key got in between); for a
-						// key that was there already the likeliest content is "seen once in this very contig end"
-						note_occurrence(reinterpret_cast<unsigned long long*>(sp + 2), cr,
-						    claimed ? (unsigned long long)kEmptyW : (((unsigned long long)cr << 32) | 1ull));
-						my_valid++;
-						inserted = true;
-					}
+					key[r] = canonical_key<KW>(W, RC, p, k, nwords * 16, mask_hi, mask_lo, &fwd_canon);
+					slot[r] = hash_to_slot(key_hash<KW>(key[r]), nslots);
+					act |= 1u << r;
+					fcm |= (uint32_t)fwd_canon << r;
 				}
 			}
+		}
+#pragma unroll
+		for (int r = 0; r < kInsertBatch; ++r) {
+			ohi[r] = olo[r] = 0;
+			if (act & (1u << r)) {
+				uint64_t* p = reinterpret_cast<uint64_t*>(table + slot[r] * kSlotBytes);
+				if (KW == 1) {
+					ohi[r] = atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)kEmptyKey, (unsigned long long)key[r].hi);
+					olo[r] = ohi[r] == kEmptyKey ? kEmptyKey : 0ull;
+				} else {
+					// memory order of the pair is (p[0], p[1]) = (hi, lo); b128 = {low 64, high 64}
+					cas128(p, kEmptyKey, kEmptyKey, key[r].hi, key[r].lo, ohi[r], olo[r]);
+				}
+			}
+		}
+		uint64_t* sp[kInsertBatch];
+		unsigned long long guess[kInsertBatch], prev[kInsertBatch];
+#pragma unroll
+		for (int r = 0; r < kInsertBatch; ++r) {
+			sp[r] = nullptr;
+			guess[r] = prev[r] = 0;
+			if (act & (1u << r)) {
+				bool claimed = ohi[r] == kEmptyKey && olo[r] == kEmptyKey;
+				const bool found = ohi[r] == key[r].hi && (KW == 1 || olo[r] == key[r].lo);
+				sp[r] = reinterpret_cast<uint64_t*>(table + slot[r] * kSlotBytes);
+				if (!claimed && !found)
+					sp[r] = find_or_claim_behind<KW>(table, nslots, slot[r], key[r].hi, key[r].lo, &claimed);
+				if (sp[r] == nullptr) {
+					fail = true;
+					act &= ~(1u << r);
+				} else {
+					if (claimed)
+						sp[r][3] = end_tag | ((uint64_t)((fcm >> r) & 1u) << kPosBits) | (g0 + r * kInsertThreads + threadIdx.x);
+					guess[r] = claimed ? (unsigned long long)kEmptyW : (((unsigned long long)cr << 32) | 1ull);
+					prev[r] = atomicCAS(reinterpret_cast<unsigned long long*>(sp[r] + 2), guess[r], note_next(guess[r], cr));
+					my_valid++;
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < kInsertBatch; ++r) {
+			if ((act & (1u << r)) && prev[r] != guess[r])
+				note_occurrence_from(reinterpret_cast<unsigned long long*>(sp[r] + 2), cr, prev[r]);
 			// 32 consecutive windows of one warp = one word of the inserted-window mask
-			const uint32_t word = __ballot_sync(0xFFFFFFFFu, inserted);
+			const uint32_t word = __ballot_sync(0xFFFFFFFFu, (act >> r) & 1u);
+			const uint32_t pb = r * kInsertThreads;
 			if ((threadIdx.x & 31) == 0 && pb + (threadIdx.x & ~31u) < nw)
 				ct.TINS[(g0 + pb + threadIdx.x) >> 5] = word;
 		}
