@@ -406,49 +406,6 @@ __device__ __forceinline__ Key128 canonical_from_forward(const Key128& f, uint32
 	return f_less ? f : r;
 }
 
-// ---------------------------------------------------------------------------------
-// Bulk asynchronous copies global -> shared memory (the TMA engine's 1-D form, cp.async.bulk) completing on an
-// mbarrier: used to stage the bytes of the NEXT read pair while the current one is worked on.
-// Source, destination and size are multiples of 16 bytes.
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p)
-{
-	return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
-}
-
-__device__ __forceinline__ void mbar_init_fence()
-{
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-// one arrival that also announces `bytes` of asynchronous copies
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
-	             "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
-	             : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-	uint32_t done = 0;
-	while (!done)
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		             : "=r"(done)
-		             : "r"(smem_addr(bar)), "r"(parity)
-		             : "memory");
-}
-
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
 {
 	return __reduce_add_sync(0xFFFFFFFFu, v);

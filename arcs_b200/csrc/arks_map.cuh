@@ -667,10 +667,9 @@ __device__ __forceinline__ void prefetch_item(const WorkRecord& rec, const MapPa
 #endif
 template <int KW>
 __device__ ARKS_PAIR_ATTR uint32_t
-warp_process_pair(const WorkRecord& rec, const MapParams& P, const char* pair_bases, WarpRegion* R, uint32_t* M, uint16_t* list,
-    uint32_t lane, LaneStats& st, PairCounters& pc)
+warp_process_pair(const WorkRecord& rec, const MapParams& P, WarpRegion* R, uint32_t* M, uint16_t* list, uint32_t lane, LaneStats& st,
+    PairCounters& pc)
 {
-	// pair_bases: where the pair's first base can be read (global memory, or its staged copy in shared memory)
 	const uint32_t pair = rec.pair, state0 = rec.state[0], state1 = rec.state[1];
 	const bool fresh = state0 == kMateUnknown;
 	const bool todo0 = fresh || state0 == kMateSlow, todo1 = fresh || state1 == kMateSlow;
@@ -680,13 +679,13 @@ warp_process_pair(const WorkRecord& rec, const MapParams& P, const char* pair_ba
 	uint32_t nn1, no1, nn2, no2;
 	__syncwarp();
 	if (l1 <= 256u && l2 <= 256u) {
-		warp_pack2(R, pair_bases, l1, pair_bases + l1, l2, lane, nn1, no1, nn2, no2);
+		warp_pack2(R, P.bases + o0, l1, P.bases + o1, l2, lane, nn1, no1, nn2, no2);
 	} else if (shortpair) {
-		warp_pack(R[0], pair_bases, l1, lane, nn1, no1);
-		warp_pack(R[1], pair_bases + l1, l2, lane, nn2, no2);
+		warp_pack(R[0], P.bases + o0, l1, lane, nn1, no1);
+		warp_pack(R[1], P.bases + o1, l2, lane, nn2, no2);
 	} else {
-		warp_classify(pair_bases, l1, lane, nn1, no1);
-		warp_classify(pair_bases + l1, l2, lane, nn2, no2);
+		warp_classify(P.bases + o0, l1, lane, nn1, no1);
+		warp_classify(P.bases + o1, l2, lane, nn2, no2);
 	}
 	uint32_t c[2] = {fresh ? 0u : state0, fresh ? 0u : state1};
 	if (!fresh || (read_ok(nn1, no1, l1, P.nmax) && read_ok(nn2, no2, l2, P.nmax))) {
@@ -770,7 +769,7 @@ warp_process_pair(const WorkRecord& rec, const MapParams& P, const char* pair_ba
 					const bool clean = (rd ? (nn2 | no2) : (nn1 | no1)) == 0;
 					warp_resolve_read<KW>(R[rd], M, list, len, total, clean, E, P, lane, tr, st);
 				} else {
-					const LongResult lr = warp_windows_long<KW>(R[0], list, pair_bases + (rd ? l1 : 0u), total, P, lane, tr, st);
+					const LongResult lr = warp_windows_long<KW>(R[0], list, P.bases + (rd ? o1 : o0), total, P, lane, tr, st);
 					tr = lr.tr;
 					st = lr.st;
 				}
@@ -867,7 +866,7 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_pairs_kernel(M
 		rec.off[1] = P.read_off[2 * pair + 1];
 		rec.off[2] = P.read_off[2 * pair + 2];
 		rec.state[0] = rec.state[1] = kMateUnknown;
-		warp_process_pair<KW>(rec, P, P.bases + rec.off[0], regions[warp], Ms[warp], lists[warp], lane, st, pc);
+		warp_process_pair<KW>(rec, P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
 	}
 	const bool l0 = lane == 0; // pair counters are warp-uniform: count them once
 	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,
@@ -1563,101 +1562,33 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 }
 
 // ---- the pairs the group kernel deferred: one warp per pair, general path -------------------
-// The bytes of a warp's NEXT pair are staged into shared memory by the copy engine (cp.async.bulk completing on an
-// mbarrier, two buffers per warp) while the current pair is worked on: packing then reads shared memory instead of
-// waiting for global loads.  Pairs longer than a staging buffer, and the last bytes of a batch (a 16-byte aligned
-// copy must not run past the end of the caller's buffer), are read from global memory as before.
-constexpr uint32_t kStageBytes = 2 * kRegionBases + 32;
-
-struct StagePlan
-{
-	const char* src; // 16-byte aligned start of the copy (null: not staged)
-	uint32_t bytes;  // multiple of 16
-	uint32_t skew;   // the pair's first base sits at src + skew
-};
-
-__device__ __forceinline__ StagePlan plan_stage(const MapParams& P, uint32_t o0, uint32_t o2, const char* batch_end)
-{
-	StagePlan s{nullptr, 0, 0};
-	const char* a = P.bases + o0;
-	const char* b = P.bases + o2;
-	const uintptr_t a16 = reinterpret_cast<uintptr_t>(a) & ~uintptr_t(15);
-	const uintptr_t b16 = (reinterpret_cast<uintptr_t>(b) + 15) & ~uintptr_t(15);
-	if (o2 > o0 && b16 - a16 <= kStageBytes && b16 <= reinterpret_cast<uintptr_t>(batch_end)) {
-		s.src = reinterpret_cast<const char*>(a16);
-		s.bytes = (uint32_t)(b16 - a16);
-		s.skew = (uint32_t)(reinterpret_cast<uintptr_t>(a) - a16);
-	}
-	return s;
-}
-
 template <int KW>
 __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_slow_kernel(MapParams P)
 {
 	__shared__ WarpRegion regions[kMapWarps][2];
 	__shared__ uint32_t Ms[kMapWarps][kMWords];
 	__shared__ uint16_t lists[kMapWarps][kRegionBases];
-	__shared__ __align__(16) char stage[kMapWarps][2][kStageBytes];
-	__shared__ __align__(8) uint64_t bars[kMapWarps][2];
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
 	LaneStats st{0, 0, 0, 0, 0};
 	PairCounters pc{0, 0, 0, 0, 0, false};
 	const uint32_t n_work = *P.work_count;
 	const uint32_t nwarps = gridDim.x * kMapWarps;
-	const char* const batch_end = P.bases + P.read_off[2ull * P.n_pairs];
 	__shared__ WorkRecord recs[kMapWarps];
-	if (lane == 0) {
-		mbar_init(&bars[warp][0], 1);
-		mbar_init(&bars[warp][1], 1);
-		mbar_init_fence();
-	}
-	__syncwarp();
-	uint32_t phase[2] = {0, 0}; // parity of the next completion of each buffer
-	uint32_t buf = 0;
-	// prologue: this warp's first pair
-	StagePlan cur{nullptr, 0, 0};
-	{
-		const uint32_t i0 = blockIdx.x * kMapWarps + warp;
-		if (i0 < n_work) {
-			cur = plan_stage(P, P.work[i0].off[0], P.work[i0].off[2], batch_end);
-			if (cur.src && lane == 0) {
-				mbar_arrive_expect_tx(&bars[warp][0], cur.bytes);
-				bulk_copy_g2s(stage[warp][0], cur.src, cur.bytes, &bars[warp][0]);
-			}
-		}
-	}
 #pragma unroll 1
 	for (uint32_t i = blockIdx.x * kMapWarps + warp; i < n_work; i += nwarps) {
 		// software pipeline over work items: the record two items ahead is prefetched by address; the
-		// next item's record (an L1 hit by now) tells which lines ITS contig text and masks live in, and those are
-		// prefetched -- and its read bytes staged -- while the current item is processed.
+		// next item's record (an L1 hit by now) tells which lines ITS mates, contig text and masks live
+		// in, and those are prefetched while the current item is processed.
 		if (i + 2 * nwarps < n_work && lane == 0)
 			prefetch_l1(P.work + i + 2 * nwarps);
-		StagePlan nxt{nullptr, 0, 0};
-		if (i + nwarps < n_work) {
-			const WorkRecord& nr = P.work[i + nwarps];
-			prefetch_item(nr, P, lane);
-			nxt = plan_stage(P, nr.off[0], nr.off[2], batch_end);
-			__syncwarp(); // every lane is done reading the other buffer (it held the previous pair)
-			if (nxt.src && lane == 0) {
-				mbar_arrive_expect_tx(&bars[warp][buf ^ 1], nxt.bytes);
-				bulk_copy_g2s(stage[warp][buf ^ 1], nxt.src, nxt.bytes, &bars[warp][buf ^ 1]);
-			}
-		}
+		if (i + nwarps < n_work)
+			prefetch_item(P.work[i + nwarps], P, lane);
 		__syncwarp();
 		if (lane < 4)
 			reinterpret_cast<uint4*>(&recs[warp])[lane] = reinterpret_cast<const uint4*>(P.work + i)[lane];
 		__syncwarp();
-		const char* pair_bases = P.bases + recs[warp].off[0];
-		if (cur.src) {
-			mbar_wait(&bars[warp][buf], phase[buf]);
-			phase[buf] ^= 1u;
-			pair_bases = stage[warp][buf] + cur.skew;
-		}
-		warp_process_pair<KW>(recs[warp], P, pair_bases, regions[warp], Ms[warp], lists[warp], lane, st, pc);
-		cur = nxt;
-		buf ^= 1u;
+		warp_process_pair<KW>(recs[warp], P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
 	}
 	const bool l0 = lane == 0;
 	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,

@@ -37,7 +37,7 @@ CONFIGS = {
     "c2": dict(
         title="synthetic 50 Mbp draft (5k contigs) + 50M interleaved linked reads, k=60, j=0.55",
         genome=50_000_000, contigs=5000, pairs=25_000_000, read_len=150, k=60, j=0.55, kind="linked", ppb=250, mols=10,
-        mol_len=50000, shuffled=False, min_mult=50, max_mult=10000, min_reads=5, batch_pairs=1_562_500, cpu_genome=50_000_000),
+        mol_len=50000, shuffled=False, min_mult=50, max_mult=10000, min_reads=5, batch_pairs=3_125_000, cpu_genome=50_000_000),
     "c3": dict(
         title="E. coli-scale 5 Mbp draft + 10M stLFR-style barcoded reads, k=40, -m 2-10000",
         genome=5_000_000, contigs=100, pairs=5_000_000, read_len=150, k=40, j=0.55, kind="linked", ppb=10, mols=1,
