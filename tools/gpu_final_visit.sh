@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # final one-GPU visit of the round: the whole GPU suite, sanitizers, smoke, default bench lines, gzip input at scale
 mkdir -p gpurun_out
-O=gpurun_out/r2m
+O=gpurun_out/final
 (timeout 1500 python -m pytest tests -m gpu -q -x) > $O.pytest.log 2>&1
 echo "pytest rc=$?"; tail -4 $O.pytest.log
 for tool in racecheck synccheck; do
