@@ -26,7 +26,15 @@ def say(*a):
 
 
 tmp = tempfile.mkdtemp(prefix='abgz_')
-fa, fq, mult, windows = bench.write_cpu_sample(np, tmp, 10_000_000, pairs, 7)
+import torch  # noqa: E402
+
+dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+cfg = dict(bench.CONFIGS["c2"], genome=10_000_000, contigs=1000, name="c2")
+genome, starts, ends = bench.make_draft(torch, dev, cfg["genome"], cfg["contigs"], seed=7)
+bases, barcode, _ = bench.make_reads(torch, dev, genome, cfg, pairs, seed=8)
+fa, fq = os.path.join(tmp, "draft.fa"), os.path.join(tmp, "reads.fq")
+bench.write_draft_fasta(fa, genome.cpu().numpy(), starts, ends)
+bench.write_fastq(np, fq, bases.view(-1, cfg["read_len"]).cpu().numpy(), barcode.cpu().numpy(), cfg["read_len"])
 subprocess.check_call(['gzip', '-1', '-f', fq])
 gz = fq + '.gz'
 say('sample: %d pairs, %.2f GB compressed' % (pairs, os.path.getsize(gz) / 1e9))
