@@ -1088,6 +1088,21 @@ __device__ __noinline__ void dilate_row_call(uint32_t* X, uint32_t nmw, uint32_t
 	dilate_row(X, nmw, k);
 }
 
+// the group a warp takes after `group`: its next one in a fixed stride, or (ARKS_DYNAMIC_GROUPS) the next one nobody
+// has taken yet (a ticket counter behind the work-list counter), which evens out groups of different cost at the
+// end of a launch
+__device__ __forceinline__ uint32_t next_group(const MapParams& P, uint32_t lane, uint32_t nwarps, uint32_t group)
+{
+#ifdef ARKS_DYNAMIC_GROUPS
+	uint32_t t = 0;
+	if (lane == 0)
+		t = atomicAdd(P.work_count + 1, 1u);
+	return nwarps + __shfl_sync(0xFFFFFFFFu, t, 0);
+#else
+	return group + nwarps;
+#endif
+}
+
 template <int KW>
 __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_kernel(MapParams P)
 {
@@ -1099,7 +1114,7 @@ __global__ void __launch_bounds__(kGroupThreads, kGroupMinBlocks) map_groups_ker
 	const uint32_t n_groups = (P.n_pairs + kGroupPairs - 1) / kGroupPairs;
 	const uint32_t nwarps = gridDim.x * kGroupWarps;
 #pragma unroll 1
-	for (uint32_t group = blockIdx.x * kGroupWarps + (threadIdx.x >> 5); group < n_groups; group += nwarps) {
+	for (uint32_t group = blockIdx.x * kGroupWarps + (threadIdx.x >> 5); group < n_groups; group = next_group(P, lane, nwarps, group)) {
 		const uint32_t pair0 = group * kGroupPairs;
 		const uint32_t my_pair = pair0 + (lane >> 1);
 		const bool exists = my_pair < P.n_pairs;
