@@ -364,7 +364,7 @@ int launch_map(arks_handle* h, const char* d_bases, const uint32_t* d_off, const
 			return rcw;
 		P.work = (WorkRecord*)h->work.p;
 		P.work_count = h->d_work_count;
-		CU(cudaMemsetAsync(h->d_work_count, 0, 8, h->stream)); // [0] deferred pairs, [1] group tickets
+		CU(cudaMemsetAsync(h->d_work_count, 0, 12, h->stream)); // [0] deferred pairs, [1] group tickets, [2] work-item tickets
 		const uint64_t groups = ((uint64_t)n_pairs + kGroupPairs - 1) / kGroupPairs;
 		int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((groups + kGroupWarps - 1) / kGroupWarps, (uint64_t)h->group_grid));
 		const size_t smem = sizeof(GroupSmem) * kGroupWarps;
@@ -673,7 +673,7 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		else
 			CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, map_slow_kernel<2>, kMapThreads, 0));
 		h->slow_grid = h->sm_count * std::max(1, per_sm_s);
-		CUC(cudaMalloc(&h->d_work_count, 8));
+		CUC(cudaMalloc(&h->d_work_count, 16));
 		if (const char* s = getenv("ARKS_MAP_MODE"))
 			h->map_mode_pair = strcmp(s, "pair") == 0;
 	}

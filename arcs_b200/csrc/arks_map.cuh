@@ -1088,12 +1088,12 @@ __device__ __noinline__ void dilate_row_call(uint32_t* X, uint32_t nmw, uint32_t
 	dilate_row(X, nmw, k);
 }
 
-// the group a warp takes after `group`: its next one in a fixed stride, or (ARKS_DYNAMIC_GROUPS) the next one nobody
-// has taken yet (a ticket counter behind the work-list counter), which evens out groups of different cost at the
-// end of a launch
+// the group a warp takes after `group`: the next one nobody has taken yet (a ticket counter behind the work-list
+// counter), which evens out groups of different cost -- +5 % on configs[1], +3 % on configs[2] against a fixed stride
+// (-DARKS_STATIC_GROUPS, kept for A/B runs)
 __device__ __forceinline__ uint32_t next_group(const MapParams& P, uint32_t lane, uint32_t nwarps, uint32_t group)
 {
-#ifdef ARKS_DYNAMIC_GROUPS
+#ifndef ARKS_STATIC_GROUPS
 	uint32_t t = 0;
 	if (lane == 0)
 		t = atomicAdd(P.work_count + 1, 1u);
@@ -1590,20 +1590,44 @@ __global__ void __launch_bounds__(kMapThreads, kMapMinBlocks) map_slow_kernel(Ma
 	const uint32_t n_work = *P.work_count;
 	const uint32_t nwarps = gridDim.x * kMapWarps;
 	__shared__ WorkRecord recs[kMapWarps];
+	// work items are handed out by a ticket counter (they differ a lot in cost); a warp holds its next two tickets
+	// so that the software pipeline below knows what comes: the record two items ahead is prefetched by address; the
+	// next item's record (an L1 hit by now) tells which lines ITS mates, contig text and masks live in, and those
+	// are prefetched while the current item is processed.
+	auto take = [&]() -> uint32_t {
+#ifndef ARKS_STATIC_GROUPS
+		uint32_t t = 0;
+		if (lane == 0)
+			t = atomicAdd(P.work_count + 2, 1u);
+		return nwarps + __shfl_sync(0xFFFFFFFFu, t, 0);
+#else
+		return 0xFFFFFFFFu;
+#endif
+	};
+	uint32_t i = blockIdx.x * kMapWarps + warp;
+#ifndef ARKS_STATIC_GROUPS
+	uint32_t i1 = i < n_work ? take() : 0xFFFFFFFFu, i2 = i1 < n_work ? take() : 0xFFFFFFFFu;
+#else
+	uint32_t i1 = i + nwarps, i2 = i + 2 * nwarps;
+#endif
 #pragma unroll 1
-	for (uint32_t i = blockIdx.x * kMapWarps + warp; i < n_work; i += nwarps) {
-		// software pipeline over work items: the record two items ahead is prefetched by address; the
-		// next item's record (an L1 hit by now) tells which lines ITS mates, contig text and masks live
-		// in, and those are prefetched while the current item is processed.
-		if (i + 2 * nwarps < n_work && lane == 0)
-			prefetch_l1(P.work + i + 2 * nwarps);
-		if (i + nwarps < n_work)
-			prefetch_item(P.work[i + nwarps], P, lane);
+	for (; i < n_work;) {
+		if (i2 < n_work && lane == 0)
+			prefetch_l1(P.work + i2);
+		if (i1 < n_work)
+			prefetch_item(P.work[i1], P, lane);
 		__syncwarp();
 		if (lane < 4)
 			reinterpret_cast<uint4*>(&recs[warp])[lane] = reinterpret_cast<const uint4*>(P.work + i)[lane];
 		__syncwarp();
 		warp_process_pair<KW>(recs[warp], P, regions[warp], Ms[warp], lists[warp], lane, st, pc);
+		i = i1;
+		i1 = i2;
+#ifndef ARKS_STATIC_GROUPS
+		i2 = i2 < n_work ? take() : 0xFFFFFFFFu;
+#else
+		i2 = i2 + nwarps;
+#endif
 	}
 	const bool l0 = lane == 0;
 	flush_counters(P, lane, st, l0 ? pc.pass : 0, l0 ? pc.fail : 0, l0 ? pc.stored : 0, l0 ? pc.invalid : 0, l0 ? pc.nogood : 0,
