@@ -597,17 +597,24 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 		CUC(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
 	}
-	// slots per key: load factor 0.5 (one probe per lookup almost always) unless the table would not leave
-	// room for the rest in device memory -- a 3 Gbp draft has 3e9 keys, 96 GB of slots at load 1 -- then as
-	// dense as 0.85 (absent keys rarely reach the table: the membership filter answers first)
+	// slots per key.  Every step of a probe sequence is a dependent memory round trip for one lane of a warp, so the
+	// table is kept as sparse as the device's memory comfortably allows (configs[1], 12.5 M pairs: load 0.7 1.62,
+	// 0.5 1.78, 0.35 1.85, 0.25 1.88 x 1e11 k-mers/s): 0.25 if that takes at most 45 % of the free memory, else 0.35
+	// (60 %), else 0.5 (80 %), else as dense as it has to be, up to 0.85 -- a 3 Gbp draft has 3e9 keys, 96 GB of slots
+	// at load 1 (absent keys rarely reach the table: the membership filter answers first)
 	double load = 0.5;
 	{
 		size_t free_b = 0, total_b = 0;
 		CUC(cudaMemGetInfo(&free_b, &total_b));
-		const double budget = 0.8 * (double)free_b; // the rest: filter, packed text, build scratch, read batches, tallies
-		const double want = (double)max_kmers / load * kSlotBytes;
-		if (want > budget)
-			load = std::min(0.85, (double)max_kmers * kSlotBytes / budget);
+		const double dense = (double)max_kmers * kSlotBytes; // bytes at load 1
+		if (dense / 0.25 <= 0.45 * (double)free_b)
+			load = 0.25;
+		else if (dense / 0.35 <= 0.60 * (double)free_b)
+			load = 0.35;
+		else if (dense / 0.5 <= 0.80 * (double)free_b)
+			load = 0.5;
+		else // the rest (20 %): filter, packed text, build scratch, read batches, tallies
+			load = std::min(0.85, dense / (0.80 * (double)free_b));
 	}
 	if (const char* s = getenv("ARKS_TABLE_LOAD")) {
 		double v = atof(s);
