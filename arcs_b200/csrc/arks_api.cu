@@ -599,15 +599,17 @@ int arks_create(int device, int k, uint64_t max_kmers, arks_handle** out)
 	}
 	// slots per key.  Every step of a probe sequence is a dependent memory round trip for one lane of a warp, so the
 	// table is kept as sparse as the device's memory comfortably allows (configs[1], 12.5 M pairs: load 0.7 1.62,
-	// 0.5 1.78, 0.35 1.85, 0.25 1.88 x 1e11 k-mers/s): 0.25 if that takes at most 45 % of the free memory, else 0.35
-	// (60 %), else 0.5 (80 %), else as dense as it has to be, up to 0.85 -- a 3 Gbp draft has 3e9 keys, 96 GB of slots
+	// 0.5 1.78, 0.35 1.85, 0.25 1.88, 0.125 1.92 x 1e11 k-mers/s): 0.125 if that takes at most a quarter of the free
+	// memory, else 0.25 (45 %), else 0.35 (60 %), else 0.5 (80 %), else as dense as it has to be, up to 0.85 -- a 3 Gbp draft has 3e9 keys, 96 GB of slots
 	// at load 1 (absent keys rarely reach the table: the membership filter answers first)
 	double load = 0.5;
 	{
 		size_t free_b = 0, total_b = 0;
 		CUC(cudaMemGetInfo(&free_b, &total_b));
 		const double dense = (double)max_kmers * kSlotBytes; // bytes at load 1
-		if (dense / 0.25 <= 0.45 * (double)free_b)
+		if (dense / 0.125 <= 0.25 * (double)free_b)
+			load = 0.125;
+		else if (dense / 0.25 <= 0.45 * (double)free_b)
 			load = 0.25;
 		else if (dense / 0.35 <= 0.60 * (double)free_b)
 			load = 0.35;
