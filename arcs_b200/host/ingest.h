@@ -28,6 +28,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -41,6 +42,9 @@ namespace arks_host {
 // ---- barcodes (ids by first appearance; indexMultMap of the reference) -------------------------
 struct Barcodes
 {
+	// (block pipeline only: parser threads look ids up under a shared lock while the committing thread adds new
+	// barcodes under an exclusive one; every other user is single-threaded and takes no lock)
+	mutable std::shared_mutex mu;
 	std::unordered_map<std::string, uint32_t> id;
 	std::vector<std::string> name;
 	std::vector<int32_t> mult;    // indexMultMap value
@@ -273,6 +277,7 @@ struct Block
 	bool regular = false;
 	std::vector<std::string> local_barcodes; // block-local barcode table ...
 	std::vector<int32_t> local_counts;       // ... and the number of records carrying each (readBarcodes' count)
+	std::vector<uint32_t> global_hint;       // ... and the global id of each, if the parser thread found it known already
 	size_t records = 0, skipped_unpaired = 0, emptybarcode = 0, invalidbarcode = 0, skipped_badmult = 0;
 	std::string messages;
 };
@@ -524,11 +529,12 @@ class ParallelIngest
 	// Returns false if the file cannot be opened.
 	// `src`: an already opened stream to read instead of `path` (e.g. long reads cut on the fly, long_cut.h).
 	bool start(const std::string& path, const IngestConfig& cfg, const ParallelIngestOptions& opt, const Barcodes* frozen,
-	    std::unique_ptr<ByteSource> src = nullptr)
+	    std::unique_ptr<ByteSource> src = nullptr, const Barcodes* live = nullptr)
 	{
 		m_cfg = cfg;
 		m_opt = opt;
 		m_frozen = frozen;
+		m_live = live;
 		if (src) {
 			m_src = std::move(src);
 			return launch();
@@ -605,8 +611,21 @@ class ParallelIngest
 			// multiplicities and global barcode ids
 			if (!m_cfg.mult_known) {
 				gid.resize(b->local_barcodes.size());
+				{
+					// barcodes the parser thread did not find: one exclusive section per block
+					bool any_unknown = false;
+					for (size_t i = 0; i < gid.size(); ++i) {
+						gid[i] = i < b->global_hint.size() ? b->global_hint[i] : UINT32_MAX;
+						any_unknown |= gid[i] == UINT32_MAX;
+					}
+					if (any_unknown) {
+						std::unique_lock<std::shared_mutex> lk(bc.mu);
+						for (size_t i = 0; i < gid.size(); ++i)
+							if (gid[i] == UINT32_MAX)
+								gid[i] = bc.intern(b->local_barcodes[i]);
+					}
+				}
 				for (size_t i = 0; i < gid.size(); ++i) {
-					gid[i] = bc.intern(b->local_barcodes[i]);
 					if (counting) {
 						bc.mult[gid[i]] += b->local_counts[i];
 						bc.counted[gid[i]] = 1;
@@ -831,6 +850,17 @@ class ParallelIngest
 				m_todo.pop_front();
 			}
 			parse_block(*b, m_cfg, m_cfg.mult_known ? m_frozen : nullptr);
+			if (b->regular && !m_cfg.mult_known && m_live && !b->local_barcodes.empty()) {
+				// barcodes the run has met before are resolved here, in parallel (stLFR-style files carry thousands of
+				// distinct barcodes per block: left to the committing thread alone they bound the whole ingest)
+				b->global_hint.assign(b->local_barcodes.size(), UINT32_MAX);
+				std::shared_lock<std::shared_mutex> lk(m_live->mu);
+				for (size_t i = 0; i < b->local_barcodes.size(); ++i) {
+					auto it = m_live->id.find(b->local_barcodes[i]);
+					if (it != m_live->id.end())
+						b->global_hint[i] = it->second;
+				}
+			}
 			{
 				std::lock_guard<std::mutex> lk(m_mu);
 				m_parsed[b->seq] = std::move(b);
@@ -842,6 +872,7 @@ class ParallelIngest
 	IngestConfig m_cfg;
 	ParallelIngestOptions m_opt;
 	const Barcodes* m_frozen = nullptr;
+	const Barcodes* m_live = nullptr; // the run's barcode table, read under its shared lock (one-pass mode)
 	int m_fd = -1;
 	std::unique_ptr<ByteSource> m_src; // gzip files and pipes
 	const char* m_map = nullptr;
@@ -865,7 +896,7 @@ inline bool ingest_parallel_blocks(const std::string& path, Barcodes& bc, const 
     PairSink& sink, ParallelIngestOptions& opt, size_t* n_fast_blocks = nullptr, std::unique_ptr<ByteSource> src = nullptr)
 {
 	ParallelIngest pi;
-	if (!pi.start(path, cfg, opt, cfg.mult_known ? &bc : nullptr, std::move(src)))
+	if (!pi.start(path, cfg, opt, cfg.mult_known ? &bc : nullptr, std::move(src), cfg.mult_known ? nullptr : &bc))
 		return false;
 	pi.finish(bc, counting, ctr, sink, n_fast_blocks);
 	return true;
