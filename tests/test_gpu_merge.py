@@ -139,3 +139,45 @@ def test_nccl_merge_over_real_devices(world, tmp_path):
         assert np.array_equal(got["a"], oa) and np.array_equal(got["b"], ob) and np.array_equal(got["c"], oc)
         digests.add(tuple(got["d"].tolist()))
     assert len(digests) == 1
+
+
+def test_pair_links_with_millions_of_rows(monkeypatch):
+    """the pair-link stage at scale: 2 000 barcodes x 110 contigs each -> 12 M pair events, ~4 M distinct pairs; the
+    device's hash (grown twice from a deliberately small start), multi-tile radix sort and row gather against a numpy
+    restatement of pairContigs' counting (Arcs.cpp:1384-1432) -- rows, order and all four orientation counters"""
+    import arcs_b200 as A
+    rng = np.random.default_rng(5)
+    n_ct, n_bc, per = 3000, 2000, 110
+    idx = A.ArksIndex(32, 1024)
+    seq = synth.ACGT[rng.integers(0, 4, 600)]
+    idx.add_ends(seq, np.array([0, 300, 600], dtype=np.uint64), np.array([1, 2], dtype=np.uint32))
+    idx.finalize()
+    bcs, cts, heads, tails = [], [], [], []
+    for b in range(n_bc):
+        c = rng.choice(n_ct, per, replace=False)
+        h = rng.integers(0, 2, per) * 9  # 9 reads on one end, none on the other: always valid at -c 5, r 0.05
+        bcs.append(np.full(per, b)), cts.append(c), heads.append(h), tails.append(9 - h)
+    bcs, cts, heads, tails = (np.concatenate(x).astype(np.uint32) for x in (bcs, cts, heads, tails))
+    idx.imap_add(bcs, cts, heads, tails)
+    rank = rng.permutation(n_ct).astype(np.uint32)
+    mult = np.full(n_bc, 100, dtype=np.int32)
+    monkeypatch.setenv("ARKS_PMAP_INITIAL_SLOTS", str(1 << 21))
+    a, b, c = idx.pair_links(mult, 50, 10000, 5, 0.05, rank)
+    # numpy restatement: per barcode all unordered pairs, ordered by rank, orientation 2*(!Ahead)+(!Bhead)
+    iu, ju = np.triu_indices(per, 1)
+    C = cts.reshape(n_bc, per)
+    H = (heads.reshape(n_bc, per) > 0)
+    ci, cj, hi, hj = C[:, iu].ravel(), C[:, ju].ravel(), H[:, iu].ravel(), H[:, ju].ravel()
+    first = rank[ci] < rank[cj]
+    ra, rb = np.where(first, rank[ci], rank[cj]).astype(np.int64), np.where(first, rank[cj], rank[ci]).astype(np.int64)
+    ah, bh = np.where(first, hi, hj), np.where(first, hj, hi)
+    orient = 2 * (~ah).astype(np.int64) + (~bh).astype(np.int64)
+    key = (ra << 32) | rb
+    uk, inv = np.unique(key, return_inverse=True)
+    want = np.zeros((len(uk), 4), dtype=np.uint32)
+    np.add.at(want, (inv, orient), 1)
+    inv_rank = np.argsort(rank).astype(np.uint32)
+    assert len(a) == len(uk) > 3_000_000
+    assert np.array_equal(a, inv_rank[uk >> 32]) and np.array_equal(b, inv_rank[uk & 0xFFFFFFFF])
+    assert np.array_equal(c, want)
+    assert int(c.sum()) == n_bc * per * (per - 1) // 2
