@@ -21,6 +21,9 @@
 #include "fast_inflate.h"
 
 #include <atomic>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 #include <cstdlib>
 #include <functional>
 #include <memory>
@@ -388,6 +391,40 @@ inline uint64_t find_block_start(const uint8_t* base, size_t nbytes, uint64_t fr
 } // namespace pinf
 
 // The gzip member [in, in + n) decompressed by `threads` threads; pull-driven like FastInflate.
+// symbols -> bytes: a symbol below 256 is the byte itself, anything else names a byte of the 32 KB window in front of
+// the chunk.  Past the first stretch of a chunk nearly every symbol is a plain byte: 32 at a time when they all are.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) inline size_t translate_symbols_avx2(const uint16_t* s, size_t n, const uint8_t* w, uint8_t* o)
+{
+	size_t k = 0;
+	const __m256i hi = _mm256_set1_epi16((short)0xFF00);
+	for (; k + 32 <= n; k += 32) {
+		const __m256i a = _mm256_loadu_si256((const __m256i*)(s + k));
+		const __m256i b = _mm256_loadu_si256((const __m256i*)(s + k + 16));
+		if (_mm256_testz_si256(_mm256_or_si256(a, b), hi)) {
+			// packus works per 128-bit lane: put the four quarters back in order
+			const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xD8);
+			_mm256_storeu_si256((__m256i*)(o + k), p);
+		} else {
+			for (size_t i = k; i < k + 32; ++i)
+				o[i] = s[i] < 256 ? (uint8_t)s[i] : w[s[i] - 256];
+		}
+	}
+	return k;
+}
+#endif
+inline void translate_symbols(const uint16_t* s, size_t n, const uint8_t* w, uint8_t* o)
+{
+	size_t k = 0;
+#if defined(__x86_64__) && defined(__GNUC__)
+	static const bool have_avx2 = __builtin_cpu_supports("avx2");
+	if (have_avx2)
+		k = translate_symbols_avx2(s, n, w, o);
+#endif
+	for (; k < n; ++k)
+		o[k] = s[k] < 256 ? (uint8_t)s[k] : w[s[k] - 256];
+}
+
 class ParInflate
 {
   public:
@@ -684,8 +721,7 @@ class ParInflate
 					c.bytes.resize(c.n_sym);
 					const uint16_t* s = c.sym.p;
 					uint8_t* o = c.bytes.data();
-					for (size_t k = 0, n = c.n_sym; k < n; ++k)
-						o[k] = s[k] < 256 ? (uint8_t)s[k] : w[s[k] - 256];
+					translate_symbols(s, c.n_sym, w, o);
 					c.crc = (uint32_t)crc32_z(0, o, c.bytes.size());
 				});
 		}
