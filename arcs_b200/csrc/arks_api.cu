@@ -921,10 +921,12 @@ int arks_index_finalize(arks_handle* h, arks_index_stats* stats)
 		if (c.probe_fail)
 			return fail(h, ARKS_E_CAPACITY, "index table full: more distinct k-mers than max_kmers allows");
 		if (h->bloom_bits_per_key > 0 && c.kmers_valid > 0) {
-			// a dense table (huge drafts: load above 0.6) makes every false positive of the filter a long walk over
-			// occupied slots: twice the bits per key then (the filter is far from L2-resident at that size anyway)
+			// a dense table (huge drafts: load 0.5 and above) makes every false positive of the filter a walk over
+			// occupied slots: twice the bits per key then -- the filter is far from L2-resident at that size anyway
+			// (2 Gbp draft, load 0.5: 1.59 -> 1.65e11 k-mers/s; with a sparse table the wider filter only costs
+			// locality: c5, load 0.25: 3.90 -> 3.84e10)
 			int bits = h->bloom_bits_per_key;
-			if (!getenv("ARKS_BLOOM_BITS") && (double)c.kmers_valid > 0.6 * (double)h->nslots)
+			if (!getenv("ARKS_BLOOM_BITS") && (double)c.kmers_valid > 0.45 * (double)h->nslots)
 				bits *= 2;
 			h->bloom_words = std::max<uint64_t>(1024, (c.kmers_valid * (uint64_t)bits + 63) / 64);
 			CU(cudaMalloc(&h->bloom, h->bloom_words * 8));
