@@ -854,11 +854,14 @@ class ParallelIngest
 				// barcodes the run has met before are resolved here, in parallel (stLFR-style files carry thousands of
 				// distinct barcodes per block: left to the committing thread alone they bound the whole ingest)
 				b->global_hint.assign(b->local_barcodes.size(), UINT32_MAX);
-				std::shared_lock<std::shared_mutex> lk(m_live->mu);
-				for (size_t i = 0; i < b->local_barcodes.size(); ++i) {
-					auto it = m_live->id.find(b->local_barcodes[i]);
-					if (it != m_live->id.end())
-						b->global_hint[i] = it->second;
+				// (the lock is given up every few hundred look-ups so that the committing thread never waits long)
+				for (size_t i0 = 0; i0 < b->local_barcodes.size(); i0 += 256) {
+					std::shared_lock<std::shared_mutex> lk(m_live->mu);
+					for (size_t i = i0; i < std::min(b->local_barcodes.size(), i0 + 256); ++i) {
+						auto it = m_live->id.find(b->local_barcodes[i]);
+						if (it != m_live->id.end())
+							b->global_hint[i] = it->second;
+					}
 				}
 			}
 			{
